@@ -1,0 +1,199 @@
+/* ctdr_b200.h — C ABI of the B200-native differentiable mesh forward projector.
+ *
+ * Drop-in boundary for ONE path of jakeoung/ShapeFromProjections (package `ctdr`): the native
+ * module `cuda_diff_fp` (ctdr/cuda/diff_fp.cpp:131-134) behind `ctdr.function.rasterizer.Rasterizer`
+ * and the per-angle vertex stage of `ctdr.nn.fp_vecs.FP` / `ctdr.nn.fp_opengl.FP`.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer on the current
+ *     CUDA device unless its name ends in `_host`;
+ *   - the caller owns and allocates every buffer (as in the reference, diff_fp.cpp:21-26 /
+ *     rasterizer.py:36-46); the library allocates nothing. Scratch memory is a caller-provided
+ *     `workspace` whose size comes from the matching `*_workspace_bytes` query;
+ *   - work is enqueued on `stream` (a cudaStream_t) and returns without synchronising
+ *     (the reference launches on the legacy default stream: diff_fp_for.cu:253);
+ *   - return value: 0 ok, < 0 argument error (CTDR_E_*), > 0 a cudaError_t; a thread-local
+ *     message is available from ctdr_last_error();
+ *   - re-entrant, no global state besides that thread-local string;
+ *   - fp32 only on the device (the reference also dispatches double, diff_fp_for.cu:251; the
+ *     fp64 instantiation lives in the CPU oracle as the high-precision referee);
+ *   - sinogram / counts are [B,H,W] row-major (the reference's [B,H,W,1]); pixel offsets are 64-bit.
+ *
+ * Deviations from the reference kernels, all documented in DESIGN.md:
+ *   - the live device assert `bary > 0` (diff_fp_for.cu:183) is replaced by a counter
+ *     (stats[CTDR_STAT_NONPOSITIVE_LEN]);
+ *   - faces with label_in < label_out are skipped in every pass (the reference records them in
+ *     pass 2 only and overruns the pixel's CSR slot: diff_fp_for.cu:161-163 vs :208-218);
+ *   - `im` / `cnt` need not arrive zeroed for ctdr_raster_forward (every pixel is stored once).
+ */
+#ifndef CTDR_B200_H
+#define CTDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTDR_ABI_VERSION 1
+
+/* argument errors */
+#define CTDR_E_NULL      (-1)   /* a required pointer is NULL */
+#define CTDR_E_SHAPE     (-2)   /* a size is out of range (B,F,H,W,n_mus <= 0, H or W > 32767 ...) */
+#define CTDR_E_WORKSPACE (-3)   /* workspace too small */
+#define CTDR_E_GEOMETRY  (-4)   /* unknown geometry kind */
+
+/* flags (bit field) */
+#define CTDR_FLAG_NO_PREFILTER 1u   /* evaluate the fp64 barycentric divide for every bbox candidate
+                                       (debug; results are identical with and without) */
+#define CTDR_FLAG_DETERMINISTIC 2u  /* backward: face-owner kernel, single writer per gradient
+                                       element, fixed summation order (slower, bit-reproducible) */
+
+/* indices into the optional `stats` array (device, int64[CTDR_STAT_COUNT], caller zeroes it) */
+#define CTDR_STAT_NONPOSITIVE_LEN 0 /* fragments whose interpolated length was <= 0 (reference: trap) */
+#define CTDR_STAT_FRAGMENTS       1 /* covered (pixel, face) pairs == the reference's `vf` (rasterizer.py:64) */
+#define CTDR_STAT_CANDIDATES      2 /* bbox (pixel, face) pairs evaluated */
+#define CTDR_STAT_LIST_SEGMENTS   3 /* extra chunk-list segments taken (0 unless > capacity chunks hit a region) */
+#define CTDR_STAT_COUNT           8
+
+/* geometry kinds for the vertex stage */
+#define CTDR_GEOM_PARALLEL3D     0  /* ctdr/nn/fp_opengl.py (type "parallel3d"); geom = angles[nangles] */
+#define CTDR_GEOM_PARALLEL3D_VEC 1  /* ctdr/nn/fp_vecs.py  (type "parallel3d_vec"); geom = Vectors[nangles,12] */
+#define CTDR_GEOM_CONE_VEC       2  /* ctdr/nn/fp_vecs.py  (type "cone_vec");       geom = Vectors[nangles,12] */
+
+typedef struct CUstream_st* ctdr_stream_t;   /* == cudaStream_t */
+
+int         ctdr_abi_version(void);
+const char* ctdr_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rasterizer boundary — replaces cuda_diff_fp.forward / backward
+ * (diff_fp.cpp:21-67,77-129 -> diff_fp_for.cu:226-274, diff_fp_back.cu:297-350) together with the
+ * host logic of Rasterizer.forward/backward around them (rasterizer.py:23-32 bbox, :63-73 CSR).
+ * Inputs are the tensors the reference passes to Rasterizer.apply (rasterizer.py:13):
+ *   p6      [B,F,6]  projected vertices in detector pixels (ax,ay,bx,by,cx,cy)
+ *   ff      [B,F]    front-facing value; only its sign is used (diff_fp_for.cu:94-96)
+ *   len3    [B,F,3]  per-vertex source-to-surface lengths
+ *   labels2 [F,2]    int32 (label_in, label_out)
+ *   mus     [n_mus]  attenuation per label
+ * ------------------------------------------------------------------------------------------- */
+
+/* bytes of scratch needed by ctdr_raster_forward / ctdr_raster_backward for these sizes
+ * (chunk boxes; plus B*F floats used only by the deterministic backward) */
+size_t ctdr_raster_workspace_bytes(int B, int F, int H, int W);
+/* bytes of scratch needed by ctdr_raster_fragments (adds B*H*W cursors only when F > 49152) */
+size_t ctdr_raster_fragments_workspace_bytes(int B, int F, int H, int W);
+
+/* Pass 1 (is_the_first_pass=1): im[B,H,W] = sum over covering faces of
+ * sign*(mu_in - mu_out')*interpolated length, accumulated per pixel in ascending face order with
+ * the reference's exact arithmetic (bit-identical `im`); cnt[B,H,W] (may be NULL) = number of
+ * covering faces == cntvisible_bxhxwx1.  stats may be NULL. */
+int ctdr_raster_forward(const float* p6, const float* ff, const float* len3,
+                        const int32_t* labels2, const float* mus, int n_mus,
+                        int B, int F, int H, int W, float max_sino_val,
+                        float* im, int32_t* cnt,
+                        void* workspace, size_t workspace_bytes,
+                        int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* Pass 2 (is_the_first_pass=0): fragment list in the reference's CSR layout, for pixels whose
+ * `im` passes the reference's validity test (diff_fp_for.cu:69-73):
+ *   imidx_vf[firstidx[pix]+k] = face id + 1, imwei_3vf[3*(firstidx[pix]+k)+{0,1,2}] = (w0,w1,w2),
+ * k-th covering face in ascending face order.  Parity/debug output: the product backward
+ * recomputes coverage instead of reading this list. */
+int ctdr_raster_fragments(const float* p6, const float* ff, const float* len3,
+                          const int32_t* labels2, const float* mus, int n_mus,
+                          int B, int F, int H, int W, float max_sino_val,
+                          const float* im, const int32_t* firstidx,
+                          int32_t* imidx_vf, float* imwei_3vf,
+                          void* workspace, size_t workspace_bytes,
+                          unsigned flags, ctdr_stream_t stream);
+
+/* Backward (diff_fp_back.cu:47-295): grad_im = dL/d im [B,H,W], im = forward output (decides
+ * which pixels carry gradient, diff_fp_for.cu:69-73).  ACCUMULATES into grad_p6 [B,F,6],
+ * grad_len3 [B,F,3], grad_mus [n_mus], which must arrive zeroed (rasterizer.py:97-99).
+ * Default: warp-aggregated reductions + one atomic per (tile, face, component);
+ * CTDR_FLAG_DETERMINISTIC: single-writer kernel, no atomics on grad_p6/grad_len3. */
+int ctdr_raster_backward(const float* grad_im, const float* im,
+                         const float* p6, const float* ff, const float* len3,
+                         const int32_t* labels2, const float* mus, int n_mus,
+                         int B, int F, int H, int W, float max_sino_val,
+                         float* grad_p6, float* grad_len3, float* grad_mus,
+                         void* workspace, size_t workspace_bytes,
+                         int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Vertex stage — replaces the ~40 torch ops of FP.forward (fp_opengl.py:87-158, fp_vecs.py:85-196)
+ * and their autograd.
+ *   geom       angles[nangles] (PARALLEL3D) or Vectors[nangles,12] (the *_VEC kinds), float32,
+ *              exactly the array the reference uploads (fp_opengl.py:63, fp_vecs.py:64)
+ *   idx_angles [B] int64 rows of `geom` to project
+ *   verts [V,3] float32, faces [F,3] int32
+ *   spacing_x/y: DetectorSpacingX/Y as the Python doubles of proj_geom (PARALLEL3D only: they
+ *              define the orthographic matrix, projection.py:65-80, evaluated in double and
+ *              stored as float32 like the reference); max_sino_val: the double computed by the FP
+ *              constructor (fp_opengl.py:42, fp_vecs.py:59-62), narrowed to float32 on use.
+ * Outputs p6 [B,F,6], len3 [B,F,3], ff [B,F].
+ * ------------------------------------------------------------------------------------------- */
+int ctdr_vertex_forward(int geom_kind, const float* geom, int nangles,
+                        const int64_t* idx_angles, int B,
+                        const float* verts, int V, const int32_t* faces, int F,
+                        int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                        float* p6, float* len3, float* ff, ctdr_stream_t stream);
+
+/* Transposed Jacobian of ctdr_vertex_forward: ACCUMULATES into grad_verts [V,3] (arrives zeroed
+ * or holding a running sum).  front_facing carries no gradient (rasterizer.py:107). */
+int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles,
+                         const int64_t* idx_angles, int B,
+                         const float* verts, int V, const int32_t* faces, int F,
+                         int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                         const float* grad_p6, const float* grad_len3,
+                         float* grad_verts, ctdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused projector — mesh + geometry in, sinogram out; replaces FP.forward end to end
+ * (vertex stage -> Rasterizer -> get_valid_mask, fp_vecs.py:80-206) without materialising any
+ * [B,F,*] tensor in the caller.  Angles are processed in windows sized to `workspace_bytes`.
+ * ------------------------------------------------------------------------------------------- */
+size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_backward);
+
+int ctdr_project_forward(int geom_kind, const float* geom, int nangles,
+                         const int64_t* idx_angles, int B,
+                         const float* verts, int V, const int32_t* faces, int F,
+                         const int32_t* labels2, const float* mus, int n_mus,
+                         int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                         float* im, int32_t* cnt,
+                         void* workspace, size_t workspace_bytes,
+                         int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* grad_im [B,H,W], im [B,H,W] (forward output) -> ACCUMULATES grad_verts [V,3], grad_mus [n_mus]. */
+int ctdr_project_backward(int geom_kind, const float* geom, int nangles,
+                          const int64_t* idx_angles, int B,
+                          const float* verts, int V, const int32_t* faces, int F,
+                          const int32_t* labels2, const float* mus, int n_mus,
+                          int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                          const float* grad_im, const float* im,
+                          float* grad_verts, float* grad_mus,
+                          void* workspace, size_t workspace_bytes,
+                          int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* Projection + masked-L2 residual step of the optimiser loop (ctdr/optimize.py:162-168,190 with
+ * get_valid_mask, fp_vecs.py:10-13): phat = projector(mesh); valid = phat > -1e-6 && phat <=
+ * max_sino_val - 1e-6; loss_sum = sum_valid (target - phat)^2, n_valid = #valid; the UNNORMALISED
+ * gradient of loss_sum is accumulated into grad_verts / grad_mus (divide by n_valid — after the
+ * cross-GPU all-reduce — to get d(mean)/d·).  out2 = device float64[2] {loss_sum, n_valid}
+ * (accumulated; arrives zeroed).  phat [B,H,W] is written (needed by the reference's logging). */
+int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles,
+                               const int64_t* idx_angles, int B,
+                               const float* verts, int V, const int32_t* faces, int F,
+                               const int32_t* labels2, const float* mus, int n_mus,
+                               int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                               const float* target, float* phat,
+                               float* grad_verts, float* grad_mus, double* out2,
+                               void* workspace, size_t workspace_bytes,
+                               int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTDR_B200_H */

@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI library ``csrc/libctdr_b200.so`` (include/ctdr_b200.h).
+
+There is no CPU path and no fallback: if the shared library is missing or an entry point fails,
+the caller gets an exception.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libctdr_b200.so")
+
+FLAG_NO_PREFILTER = 1
+FLAG_DETERMINISTIC = 2
+STAT_NONPOSITIVE_LEN, STAT_FRAGMENTS, STAT_CANDIDATES, STAT_LIST_SEGMENTS, STAT_COUNT = 0, 1, 2, 3, 8
+GEOM_PARALLEL3D, GEOM_PARALLEL3D_VEC, GEOM_CONE_VEC = 0, 1, 2
+GEOM_KINDS = {"parallel3d": GEOM_PARALLEL3D, "parallel3d_vec": GEOM_PARALLEL3D_VEC, "cone_vec": GEOM_CONE_VEC}
+
+_vp, _i, _sz, _u, _d, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_uint,
+                            ctypes.c_double, ctypes.c_float)
+
+# name -> (restype, argtypes); must list every symbol declared in include/ctdr_b200.h
+SIGNATURES = {
+    "ctdr_abi_version": (_i, []),
+    "ctdr_last_error": (ctypes.c_char_p, []),
+    "ctdr_raster_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ctdr_raster_fragments_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "ctdr_raster_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_raster_fragments": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
+    "ctdr_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_vertex_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "ctdr_vertex_backward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "ctdr_project_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "ctdr_project_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
+                                  _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_project_backward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
+                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_project_residual_step": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the library once; raise (never fall back) when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m shapefromprojections_b200.csrc.build` "
+                "(there is no CPU fallback for the projector)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.ctdr_abi_version() != 1:
+            raise RuntimeError("libctdr_b200.so: unexpected ABI version")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ctdr_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_workspaces: dict = {}
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream); the C ABI never allocates."""
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")          # diff_fp.cpp:4
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: the B200 kernels are fp32 (got {t.dtype}); the fp64 instantiation of the "
+                        "reference is only available in the CPU oracle")
+    return t.contiguous()                                            # rasterizer.py:40-43

@@ -1,0 +1,508 @@
+// ctdr_b200.cu — C ABI (include/ctdr_b200.h) over the sm_100a kernels.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+// (shapefromprojections_b200/csrc/build.py).  No torch types, no allocation, no synchronisation.
+#include "../../include/ctdr_b200.h"
+#include "ctdr_raster.cuh"
+#include "ctdr_vertex.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+using namespace ctdr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define CTDR_CUDA(call, where)                                   \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where);    \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_sizes(int B, int F, int H, int W, int n_mus) {
+    if (B <= 0 || F <= 0 || H <= 0 || W <= 0 || n_mus <= 0)
+        return fail(CTDR_E_SHAPE, "sizes must be positive (B=%d F=%d H=%d W=%d n_mus=%d)", B, F, H, W, n_mus);
+    if (H > 32767 || W > 32767) return fail(CTDR_E_SHAPE, "detector larger than 32767 pixels (H=%d W=%d)", H, W);
+    if (n_mus > 4096) return fail(CTDR_E_SHAPE, "n_mus=%d > 4096", n_mus);
+    return 0;
+}
+
+int pick_region_tiles(int B, int H, int W) {
+    // one CTA per region of RT x RT tiles; shrink regions until the grid fills the 148 SMs a few times
+    int rt = 8;
+    while (rt > 2) {
+        const long long regions = (long long)((W + rt * TILE - 1) / (rt * TILE)) * ((H + rt * TILE - 1) / (rt * TILE));
+        if (regions * B >= 4LL * 148) break;
+        rt >>= 1;
+    }
+    return rt;
+}
+
+size_t raster_smem_bytes(int n_mus) { return sizeof(CtaSmem) + (size_t)n_mus * sizeof(float); }
+
+void fill_decomposition(RasterParams& P, const short4* boxes) {
+    P.NC = (P.F + CHUNK - 1) / CHUNK;
+    P.RT = pick_region_tiles(P.B, P.H, P.W);
+    P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
+    P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
+    P.chunk_box = boxes;
+}
+
+int launch_chunk_bbox(const RasterParams& P, short4* boxes, cudaStream_t st) {
+    const long long warps = (long long)P.B * P.NC;
+    const long long blocks = (warps + WARPS - 1) / WARPS;
+    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes);
+    CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
+    return 0;
+}
+
+template <int MODE>
+int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
+    const long long blocks = (long long)P.B * P.regions_x * P.regions_y;
+    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*regions too large for one launch");
+    const size_t smem = raster_smem_bytes(P.n_mus);
+    if (flags & CTDR_FLAG_NO_PREFILTER) {
+        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        k_raster<MODE, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+    } else {
+        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+    }
+    CTDR_CUDA(cudaGetLastError(), "k_raster launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic backward: one thread owns one (angle, face), walks its whole bounding box in
+// row-major order and is the only writer of its 9 gradient values; the per-face attenuation
+// terms go to `fs` and are reduced in a fixed tree by k_mus_reduce.
+// ---------------------------------------------------------------------------------------------
+template <bool PREFILTER>
+__global__ void __launch_bounds__(128)
+k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.B * P.F) return;
+    const int b = (int)(gid / P.F), f = (int)(gid % P.F);
+    fs[gid] = 0.0f;
+    const int2 lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
+    if (lab.x < lab.y) return;
+    const float2* pp = reinterpret_cast<const float2*>(P.p6 + gid * 6);
+    const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+    int ix0, iy0, ix1, iy1;
+    if (!face_int_bbox(va.x, va.y, vb.x, vb.y, vc.x, vc.y, P.H, P.W, ix0, iy0, ix1, iy1)) return;
+    const EdgeSetup es = edge_setup(va.x, va.y, vb.x, vb.y, vc.x, vc.y);
+    float M0 = 0.0f, Ms = 0.0f, Mt = 0.0f;
+    const long long base = (long long)b * P.H * P.W;
+    for (int y = iy0; y <= iy1; ++y)
+        for (int x = ix0; x <= ix1; ++x) {
+            const long long o = base + (long long)y * P.W + x;
+            const float g = __ldg(P.grad_im + o);
+            if (g == 0.0f) continue;
+            const float v = __ldg(P.im_in + o);
+            if (((double)v < -1e-5) || (v > P.msv)) continue;              // diff_fp_for.cu:69-73
+            float s, t, w0, w1, w2;
+            if (!cover_exact<PREFILTER>(es, (float)x, (float)y, s, t, w0, w1, w2)) continue;
+            M0 += g; Ms += g * s; Mt += g * t;
+        }
+    if (M0 == 0.0f && Ms == 0.0f && Mt == 0.0f) return;
+    float sgn = (__ldg(P.ff + gid) < 0.0f) ? -1.0f : 1.0f;
+    if (lab.x == lab.y) sgn = -sgn;
+    const float r0 = __ldg(P.len3 + gid * 3), r1 = __ldg(P.len3 + gid * 3 + 1), r2 = __ldg(P.len3 + gid * 3 + 2);
+    const float cgeo = sgn * (__ldg(P.mus + lab.x) - __ldg(P.mus + lab.y));
+    float gp[6], gl[3], bsum;
+    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, gp, gl, bsum);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) P.grad_p6[gid * 6 + k] += gp[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) P.grad_len3[gid * 3 + k] += gl[k];
+    fs[gid] = sgn * bsum;
+}
+
+// grad_mus[l] += sum over (b,f) of the face's attenuation term, fixed summation order:
+// each of the 1024 threads sums a strided slice sequentially, then a fixed shared-memory tree.
+__global__ void __launch_bounds__(1024)
+k_mus_reduce(const float* __restrict__ fs, const int* __restrict__ labels2, int B, int F, int n_mus,
+             float* __restrict__ grad_mus) {
+    __shared__ float sh[1024];
+    const int l = blockIdx.x;
+    float acc = 0.0f;
+    const long long n = (long long)B * F;
+    for (long long i = threadIdx.x; i < n; i += 1024) {
+        const int f = (int)(i % F);
+        const int2 lab = __ldg(reinterpret_cast<const int2*>(labels2) + f);
+        const float v = fs[i];
+        if (lab.x == l) acc += (l == 0 ? -v : v);
+        if (lab.y == l) acc += (l == 0 ? v : -v);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 512; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grad_mus[l] += sh[0];
+}
+
+struct RasterWs {
+    short4* boxes;
+    float* fs;       // deterministic backward only
+    int* cursors;    // fragment mode, multi-segment only
+};
+
+size_t raster_ws_layout(int B, int F, int H, int W, bool want_fs, bool want_cursors, RasterWs* out, void* base) {
+    const int NC = (F + CHUNK - 1) / CHUNK;
+    size_t off = 0;
+    char* p = static_cast<char*>(base);
+    if (out) out->boxes = reinterpret_cast<short4*>(p + off);
+    off += align_up((size_t)B * NC * sizeof(short4), 256);
+    if (out) out->fs = nullptr;
+    if (want_fs) {
+        if (out) out->fs = reinterpret_cast<float*>(p + off);
+        off += align_up((size_t)B * F * sizeof(float), 256);
+    }
+    if (out) out->cursors = nullptr;
+    if (want_cursors && NC > LIST_CAP) {
+        if (out) out->cursors = reinterpret_cast<int*>(p + off);
+        off += align_up((size_t)B * H * W * sizeof(int), 256);
+    }
+    return off;
+}
+
+RasterParams base_params(const float* p6, const float* ff, const float* len3, const int32_t* labels2,
+                         const float* mus, int n_mus, int B, int F, int H, int W, float msv, int64_t* stats) {
+    RasterParams P;
+    memset(&P, 0, sizeof(P));
+    P.p6 = p6; P.ff = ff; P.len3 = len3; P.labels2 = labels2; P.mus = mus; P.n_mus = n_mus;
+    P.B = B; P.F = F; P.H = H; P.W = W; P.msv = msv;
+    P.stats = reinterpret_cast<unsigned long long*>(stats);
+    return P;
+}
+
+int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream_t st) {
+    if (flags & CTDR_FLAG_DETERMINISTIC) {
+        const long long n = (long long)P.B * P.F;
+        const long long blocks = (n + 127) / 128;
+        if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+        if (flags & CTDR_FLAG_NO_PREFILTER) k_backward_faceowner<false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        else k_backward_faceowner<true><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        CTDR_CUDA(cudaGetLastError(), "k_backward_faceowner launch");
+        k_mus_reduce<<<P.n_mus, 1024, 0, st>>>(ws.fs, P.labels2, P.B, P.F, P.n_mus, P.grad_mus);
+        CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
+        return 0;
+    }
+    fill_decomposition(P, ws.boxes);
+    int rc = launch_chunk_bbox(P, ws.boxes, st);
+    if (rc) return rc;
+    return launch_raster<MODE_BWD>(P, flags, st);
+}
+
+VertexParams vertex_params(int kind, const float* geom, const int64_t* idx, int B, const float* verts, int V,
+                           const int32_t* faces, int F, int H, int W, double sx, double sy, double msv) {
+    VertexParams P;
+    memset(&P, 0, sizeof(P));
+    P.kind = kind; P.geom = geom; P.idx_angles = reinterpret_cast<const long long*>(idx);
+    P.B = B; P.V = V; P.F = F; P.H = H; P.W = W; P.verts = verts; P.faces = faces;
+    P.msv = (float)msv;
+    if (kind == CTDR_GEOM_PARALLEL3D) {
+        // ortho_Mat / compute_P (ctdr/utils/projection.py:16-30,65-80) in double, stored as float32
+        const double left = -sx * W / 2.0, bottom = -sy * H / 2.0;
+        const double half_u = 0.0 * sx, half_v = 0.5 * sy;
+        const double l = left - half_u, r = -left - half_u, bo = bottom + half_v, t = -bottom + half_v;
+        P.P00 = (float)(2.0 / (r - l));
+        P.P11 = (float)(2.0 / (t - bo));
+        P.P13 = (float)(-(t + bo) / (t - bo));
+    }
+    return P;
+}
+
+int check_geom(int kind) {
+    if (kind < 0 || kind > 2) return fail(CTDR_E_GEOMETRY, "unknown geometry kind %d", kind);
+    return 0;
+}
+
+struct ProjectWs {
+    float *p6, *len3, *ff, *gp6, *glen3;
+    void* raster;
+    size_t raster_bytes;
+    int window;   // angles per window
+};
+
+size_t project_per_angle_bytes(int F, bool bwd) {
+    const int NC = (F + CHUNK - 1) / CHUNK;
+    return (size_t)F * (40 + (bwd ? 36 : 0)) + (size_t)NC * sizeof(short4);
+}
+
+int project_ws_layout(int B, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
+    const size_t slack = 8 * 256;
+    const size_t per = project_per_angle_bytes(F, bwd);
+    if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
+    long long win = (long long)((bytes - slack) / per);
+    if (win > B) win = B;
+    ws->window = (int)win;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
+    ws->len3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
+    ws->ff = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 4, 256);
+    ws->gp6 = ws->glen3 = nullptr;
+    if (bwd) {
+        ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
+        ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
+    }
+    ws->raster = p + off;
+    ws->raster_bytes = raster_ws_layout((int)win, F, H, W, false, false, nullptr, nullptr);
+    (void)H; (void)W;
+    return 0;
+}
+
+int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* ff, cudaStream_t st) {
+    const long long n = (long long)P.B * P.F;
+    const long long blocks = (n + 255) / 256;
+    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    k_vertex_forward<<<(unsigned)blocks, 256, 0, st>>>(P, p6, len3, ff);
+    CTDR_CUDA(cudaGetLastError(), "k_vertex_forward launch");
+    return 0;
+}
+
+int launch_vertex_backward(const VertexParams& P, const float* gp6, const float* glen3, float* grad_verts, cudaStream_t st) {
+    // enough angle slices to fill the machine, few enough to keep atomics per vertex low
+    int slices = 1;
+    const long long face_blocks = (P.F + 255) / 256;
+    while (slices < P.B && face_blocks * slices < 4 * 148 && slices < 64) slices <<= 1;
+    if (slices > P.B) slices = P.B;
+    const int per = (P.B + slices - 1) / slices;
+    dim3 grid((unsigned)face_blocks, (unsigned)((P.B + per - 1) / per));
+    k_vertex_backward<<<grid, 256, 0, st>>>(P, gp6, glen3, grad_verts, per);
+    CTDR_CUDA(cudaGetLastError(), "k_vertex_backward launch");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctdr_abi_version(void) { return CTDR_ABI_VERSION; }
+const char* ctdr_last_error(void) { return g_err; }
+
+size_t ctdr_raster_workspace_bytes(int B, int F, int H, int W) {
+    if (B <= 0 || F <= 0) return 0;
+    // chunk boxes + the per-face attenuation terms of the deterministic backward
+    return raster_ws_layout(B, F, H, W, true, false, nullptr, nullptr);
+}
+
+size_t ctdr_raster_fragments_workspace_bytes(int B, int F, int H, int W) {
+    if (B <= 0 || F <= 0) return 0;
+    return raster_ws_layout(B, F, H, W, false, true, nullptr, nullptr);
+}
+
+int ctdr_raster_forward(const float* p6, const float* ff, const float* len3, const int32_t* labels2,
+                        const float* mus, int n_mus, int B, int F, int H, int W, float max_sino_val,
+                        float* im, int32_t* cnt, void* workspace, size_t workspace_bytes,
+                        int64_t* stats, unsigned flags, ctdr_stream_t stream) {
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (!p6 || !ff || !len3 || !labels2 || !mus || !im || !workspace) return fail(CTDR_E_NULL, "ctdr_raster_forward: null pointer");
+    RasterWs ws;
+    const size_t need = raster_ws_layout(B, F, H, W, false, false, &ws, workspace);
+    if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+    RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, stats);
+    P.im = im; P.cnt = cnt;
+    fill_decomposition(P, ws.boxes);
+    if (int rc = launch_chunk_bbox(P, ws.boxes, stream)) return rc;
+    return launch_raster<MODE_FWD>(P, flags, stream);
+}
+
+int ctdr_raster_fragments(const float* p6, const float* ff, const float* len3, const int32_t* labels2,
+                          const float* mus, int n_mus, int B, int F, int H, int W, float max_sino_val,
+                          const float* im, const int32_t* firstidx, int32_t* imidx_vf, float* imwei_3vf,
+                          void* workspace, size_t workspace_bytes, unsigned flags, ctdr_stream_t stream) {
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (!p6 || !ff || !len3 || !labels2 || !mus || !im || !firstidx || !imidx_vf || !imwei_3vf || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_raster_fragments: null pointer");
+    RasterWs ws;
+    const size_t need = raster_ws_layout(B, F, H, W, false, true, &ws, workspace);
+    if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+    RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, nullptr);
+    P.im_in = im; P.firstidx = firstidx; P.imidx = imidx_vf; P.imwei = imwei_3vf;
+    P.cnt = ws.cursors;
+    fill_decomposition(P, ws.boxes);
+    if (int rc = launch_chunk_bbox(P, ws.boxes, stream)) return rc;
+    return launch_raster<MODE_FRAG>(P, flags, stream);
+}
+
+int ctdr_raster_backward(const float* grad_im, const float* im, const float* p6, const float* ff,
+                         const float* len3, const int32_t* labels2, const float* mus, int n_mus,
+                         int B, int F, int H, int W, float max_sino_val,
+                         float* grad_p6, float* grad_len3, float* grad_mus,
+                         void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                         ctdr_stream_t stream) {
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (!grad_im || !im || !p6 || !ff || !len3 || !labels2 || !mus || !grad_p6 || !grad_len3 || !grad_mus || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_raster_backward: null pointer");
+    RasterWs ws;
+    const bool det = (flags & CTDR_FLAG_DETERMINISTIC) != 0;
+    const size_t need = raster_ws_layout(B, F, H, W, det, false, &ws, workspace);
+    if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+    RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, stats);
+    P.grad_im = grad_im; P.im_in = im; P.grad_p6 = grad_p6; P.grad_len3 = grad_len3; P.grad_mus = grad_mus;
+    return raster_backward_impl(P, ws, flags, stream);
+}
+
+int ctdr_vertex_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                        const float* verts, int V, const int32_t* faces, int F, int H, int W,
+                        double spacing_x, double spacing_y, double max_sino_val,
+                        float* p6, float* len3, float* ff, ctdr_stream_t stream) {
+    (void)nangles;
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, 1)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !p6 || !len3 || !ff) return fail(CTDR_E_NULL, "ctdr_vertex_forward: null pointer");
+    const VertexParams P = vertex_params(geom_kind, geom, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    return launch_vertex_forward(P, p6, len3, ff, stream);
+}
+
+int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                         const float* verts, int V, const int32_t* faces, int F, int H, int W,
+                         double spacing_x, double spacing_y, double max_sino_val,
+                         const float* grad_p6, const float* grad_len3, float* grad_verts, ctdr_stream_t stream) {
+    (void)nangles;
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, 1)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !grad_p6 || !grad_len3 || !grad_verts) return fail(CTDR_E_NULL, "ctdr_vertex_backward: null pointer");
+    const VertexParams P = vertex_params(geom_kind, geom, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    return launch_vertex_backward(P, grad_p6, grad_len3, grad_verts, stream);
+}
+
+size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_backward) {
+    (void)V; (void)H; (void)W;
+    if (B <= 0 || F <= 0) return 0;
+    const size_t per = project_per_angle_bytes(F, need_backward != 0);
+    const size_t budget = (size_t)6 << 30;               // default window budget: 6 GiB
+    long long win = (long long)(budget / per);
+    if (win < 1) win = 1;
+    if (win > B) win = B;
+    return per * (size_t)win + 8 * 256;
+}
+
+int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                         const float* verts, int V, const int32_t* faces, int F,
+                         const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                         double spacing_x, double spacing_y, double max_sino_val,
+                         float* im, int32_t* cnt, void* workspace, size_t workspace_bytes,
+                         int64_t* stats, unsigned flags, ctdr_stream_t stream) {
+    (void)nangles;
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !im || !workspace) return fail(CTDR_E_NULL, "ctdr_project_forward: null pointer");
+    ProjectWs ws;
+    if (int rc = project_ws_layout(B, F, H, W, false, workspace, workspace_bytes, &ws)) return rc;
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += ws.window) {
+        const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
+        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        P.im = im + (size_t)b0 * hw;
+        P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
+        fill_decomposition(P, static_cast<short4*>(ws.raster));
+        if (int rc = launch_chunk_bbox(P, static_cast<short4*>(ws.raster), stream)) return rc;
+        if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
+    }
+    return 0;
+}
+
+static int project_backward_impl(int geom_kind, const float* geom, const int64_t* idx_angles, int B,
+                                 const float* verts, int V, const int32_t* faces, int F,
+                                 const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                                 double spacing_x, double spacing_y, double max_sino_val,
+                                 const float* grad_im, const float* im, const float* target, double* out2,
+                                 float* grad_verts, float* grad_mus,
+                                 void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                                 cudaStream_t stream) {
+    ProjectWs ws;
+    if (int rc = project_ws_layout(B, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += ws.window) {
+        const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
+        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
+        CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        P.im_in = im + (size_t)b0 * hw;
+        P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
+        fill_decomposition(P, static_cast<short4*>(ws.raster));
+        if (int rc = launch_chunk_bbox(P, static_cast<short4*>(ws.raster), stream)) return rc;
+        if (target) {
+            P.target = target + (size_t)b0 * hw;
+            P.out2 = out2;
+            P.mask_hi = (float)(max_sino_val - 1e-6);
+            if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
+        } else {
+            P.grad_im = grad_im + (size_t)b0 * hw;
+            if (int rc = launch_raster<MODE_BWD>(P, flags, stream)) return rc;
+        }
+        if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
+    }
+    return 0;
+}
+
+int ctdr_project_backward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                          const float* verts, int V, const int32_t* faces, int F,
+                          const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                          double spacing_x, double spacing_y, double max_sino_val,
+                          const float* grad_im, const float* im, float* grad_verts, float* grad_mus,
+                          void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                          ctdr_stream_t stream) {
+    (void)nangles;
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !grad_im || !im || !grad_verts || !grad_mus || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_project_backward: null pointer");
+    return project_backward_impl(geom_kind, geom, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
+                                 spacing_x, spacing_y, max_sino_val, grad_im, im, nullptr, nullptr,
+                                 grad_verts, grad_mus, workspace, workspace_bytes, stats, flags, stream);
+}
+
+int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                               const float* verts, int V, const int32_t* faces, int F,
+                               const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                               double spacing_x, double spacing_y, double max_sino_val,
+                               const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                               void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                               ctdr_stream_t stream) {
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !target || !phat || !grad_verts || !grad_mus || !out2 || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_project_residual_step: null pointer");
+    // forward over all angles first (phat is an output the caller keeps), then the residual/backward sweep
+    if (int rc = ctdr_project_forward(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus,
+                                      H, W, spacing_x, spacing_y, max_sino_val, phat, nullptr,
+                                      workspace, workspace_bytes, stats, flags, stream)) return rc;
+    return project_backward_impl(geom_kind, geom, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
+                                 spacing_x, spacing_y, max_sino_val, nullptr, phat, target, out2,
+                                 grad_verts, grad_mus, workspace, workspace_bytes, stats, flags, stream);
+}
+
+}  // extern "C"

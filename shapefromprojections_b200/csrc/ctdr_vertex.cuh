@@ -1,0 +1,237 @@
+// ctdr_vertex.cuh — per-angle vertex stage (world vertices -> detector pixels, ray lengths,
+// facing sign) and its transposed Jacobian.  Replaces the ~40 torch ops of
+//   ctdr/nn/fp_opengl.py:87-158  (geometry "parallel3d",      kind CTDR_GEOM_PARALLEL3D)
+//   ctdr/nn/fp_vecs.py:85-196    ("parallel3d_vec"/"cone_vec", kinds *_VEC)
+// and their autograd.  fp32 operations follow the reference's op order with explicit
+// round-to-nearest intrinsics (torch evaluates every op separately, so nothing is fused there);
+// results agree with the torch chain to a few ulp (exact agreement is not defined across
+// cuBLAS/torch versions — SURVEY.md section 7, hard part 1).
+#pragma once
+#include "ctdr_common.cuh"
+
+namespace ctdr {
+
+struct VertexParams {
+    int kind;
+    const float* geom;            // angles[nangles] or Vectors[nangles,12]
+    const long long* idx_angles;  // [B]
+    int B, V, F, H, W;
+    const float* verts;           // [V,3]
+    const int* faces;             // [F,3]
+    float msv;                    // max_sino_val as float32
+    float P00, P11, P13;          // orthographic matrix entries (projection.py:16-30), PARALLEL3D only
+};
+
+struct AngleConst {
+    // PARALLEL3D
+    float ct, st;
+    // *_VEC
+    float Sx, Sy, Sz, N0, N1, ux, uy, vz, DSx, DSy, DSz, coeff;
+    bool use_x;
+};
+
+__device__ __forceinline__ AngleConst angle_const(const VertexParams& P, int b) {
+    AngleConst A = {};
+    const long long row = P.idx_angles[b];
+    if (P.kind == 0) {
+        const float th = __ldg(P.geom + row);
+        A.ct = cosf(th); A.st = sinf(th);                               // fp_opengl.py:89-90
+        return A;
+    }
+    const float* g = P.geom + row * 12;
+    A.Sx = __ldg(g + 0); A.Sy = __ldg(g + 1); A.Sz = __ldg(g + 2);
+    const float Dx = __ldg(g + 3), Dy = __ldg(g + 4), Dz = __ldg(g + 5);
+    A.ux = __ldg(g + 6); A.uy = __ldg(g + 7);
+    const float uz = __ldg(g + 8), vx = __ldg(g + 9), vy = __ldg(g + 10);
+    A.vz = __ldg(g + 11);
+    A.N0 = __fmul_rn(A.uy, A.vz);                                       // fp_vecs.py:120-122
+    A.N1 = __fmul_rn(-A.ux, A.vz);
+    float px, py, pz;                                                   // det_pos
+    if (P.kind == 1) {
+        const float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(A.N0, A.N0), __fmul_rn(A.N1, A.N1)));
+        A.N0 = __fdiv_rn(A.N0, nn); A.N1 = __fdiv_rn(A.N1, nn);         // :128
+        px = __fmul_rn(-P.msv, A.Sx); py = __fmul_rn(-P.msv, A.Sy); pz = __fmul_rn(-P.msv, A.Sz);  // :73-74
+        A.coeff = 0.0f;
+    } else {
+        px = Dx; py = Dy; pz = Dz;                                      // :72
+        const float NS = __fadd_rn(__fmul_rn(A.N0, A.Sx), __fmul_rn(A.N1, A.Sy));   // :146
+        const float D = -__fadd_rn(__fmul_rn(A.N0, px), __fmul_rn(A.N1, py));       // :147
+        A.coeff = -__fadd_rn(NS, D);                                    // :148
+    }
+    const float hh = 0.5f * (float)P.H, hw = 0.5f * (float)P.W;        // :161
+    A.DSx = __fsub_rn(__fsub_rn(px, __fmul_rn(hh, vx)), __fmul_rn(hw, A.ux));
+    A.DSy = __fsub_rn(__fsub_rn(py, __fmul_rn(hh, vy)), __fmul_rn(hw, A.uy));
+    A.DSz = __fsub_rn(__fsub_rn(pz, __fmul_rn(hh, A.vz)), __fmul_rn(hw, uz));
+    A.use_x = fabsf(A.ux) > fabsf(A.uy);                                // :168
+    return A;
+}
+
+struct VertexOut {
+    float px, py, len;
+    float cx, cy, cz;   // PARALLEL3D: camera-space position; CONE: unit ray R/|R|; PARALLEL_VEC: unused
+    float t;            // *_VEC: ray parameter
+};
+
+__device__ __forceinline__ VertexOut project_vertex(const VertexParams& P, const AngleConst& A,
+                                                    float x, float y, float z) {
+    VertexOut o = {};
+    if (P.kind == 0) {
+        const float xr = __fadd_rn(__fmul_rn(x, A.ct), __fmul_rn(y, A.st));      // fp_opengl.py:91
+        const float yr = __fadd_rn(__fmul_rn(-x, A.st), __fmul_rn(y, A.ct));     // :92
+        o.cx = xr; o.cy = -z; o.cz = __fadd_rn(yr, -P.msv);                      // :103-104
+        o.len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(o.cx, o.cx), __fmul_rn(o.cy, o.cy)),
+                                     __fmul_rn(o.cz, o.cz)));                    // :107
+        const float nx = __fmul_rn(P.P00, o.cx);                                 // :111 (P03 == -0)
+        const float ny = __fadd_rn(__fmul_rn(P.P11, o.cy), P.P13);
+        o.px = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.0f), 2.0f), (float)P.W);      // :157
+        o.py = __fsub_rn(__fdiv_rn(__fmul_rn((float)P.H, __fsub_rn(1.0f, ny)), 2.0f), 0.5f);  // :158
+        return o;
+    }
+    float bx, by, bz, rx, ry, rz, t;
+    if (P.kind == 1) {
+        rx = -A.Sx; ry = -A.Sy; rz = -A.Sz;                                      // fp_vecs.py:130
+        bx = x; by = y; bz = z;                                                  // :131
+        const float NS = __fadd_rn(__fmul_rn(A.N0, x), __fmul_rn(A.N1, y));      // :132
+        const float NR = __fadd_rn(__fmul_rn(A.N0, rx), __fmul_rn(A.N1, ry));    // :135
+        t = __fdiv_rn(-__fadd_rn(NS, P.msv), NR);                                // :133,136
+        o.len = t;                                                               // :137
+    } else {
+        const float Rx = __fsub_rn(x, A.Sx), Ry = __fsub_rn(y, A.Sy), Rz = __fsub_rn(z, A.Sz);  // :141
+        o.len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(Rx, Rx), __fmul_rn(Ry, Ry)), __fmul_rn(Rz, Rz)));  // :142
+        rx = __fdiv_rn(Rx, o.len); ry = __fdiv_rn(Ry, o.len); rz = __fdiv_rn(Rz, o.len);      // :145
+        bx = A.Sx; by = A.Sy; bz = A.Sz;
+        const float NR = __fadd_rn(__fmul_rn(A.N0, rx), __fmul_rn(A.N1, ry));    // :149
+        t = __fdiv_rn(A.coeff, __fadd_rn(NR, 1e-10f));                           // :150
+    }
+    o.cx = rx; o.cy = ry; o.cz = rz; o.t = t;
+    const float Px = __fadd_rn(bx, __fmul_rn(t, rx));                            // :153
+    const float Py = __fadd_rn(by, __fmul_rn(t, ry));
+    const float Pz = __fadd_rn(bz, __fmul_rn(t, rz));
+    const float dx = __fsub_rn(Px, A.DSx), dy = __fsub_rn(Py, A.DSy), dz = __fsub_rn(Pz, A.DSz);  // :162
+    o.px = A.use_x ? __fdiv_rn(dx, A.ux) : __fdiv_rn(dy, A.uy);                  // :171-172
+    o.py = __fdiv_rn(dz, A.vz);                                                  // :173
+    return o;
+}
+
+// thread per (angle, face): p6 / len3 / ff exactly as handed to Rasterizer.apply
+__global__ void __launch_bounds__(256)
+k_vertex_forward(const VertexParams P, float* __restrict__ p6, float* __restrict__ len3,
+                 float* __restrict__ ff) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.B * P.F) return;
+    const int b = (int)(gid / P.F), f = (int)(gid % P.F);
+    const AngleConst A = angle_const(P, b);
+    const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
+    const float x0 = __ldg(P.verts + 3 * i0), y0 = __ldg(P.verts + 3 * i0 + 1), z0 = __ldg(P.verts + 3 * i0 + 2);
+    const float x1 = __ldg(P.verts + 3 * i1), y1 = __ldg(P.verts + 3 * i1 + 1), z1 = __ldg(P.verts + 3 * i1 + 2);
+    const float x2 = __ldg(P.verts + 3 * i2), y2 = __ldg(P.verts + 3 * i2 + 1), z2 = __ldg(P.verts + 3 * i2 + 2);
+    const VertexOut a = project_vertex(P, A, x0, y0, z0);
+    const VertexOut bb = project_vertex(P, A, x1, y1, z1);
+    const VertexOut c = project_vertex(P, A, x2, y2, z2);
+    float facing;
+    if (P.kind == 0) {
+        // camera-space normal, ray fixed at (0,0,-1): front_facing = -n_z (fp_opengl.py:137-148)
+        const float e1x = __fsub_rn(bb.cx, a.cx), e1y = __fsub_rn(bb.cy, a.cy);
+        const float e2x = __fsub_rn(c.cx, a.cx), e2y = __fsub_rn(c.cy, a.cy);
+        facing = -__fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    } else {
+        // world-space normal (fp_vecs.py:85-91) dotted with the ray (parallel) or R^(v0) (cone) (:191-196)
+        const float e1x = __fsub_rn(x1, x0), e1y = __fsub_rn(y1, y0), e1z = __fsub_rn(z1, z0);
+        const float e2x = __fsub_rn(x2, x0), e2y = __fsub_rn(y2, y0), e2z = __fsub_rn(z2, z0);
+        const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+        const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+        const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+        const float rx = (P.kind == 2) ? a.cx : A.Sx, ry = (P.kind == 2) ? a.cy : A.Sy, rz = (P.kind == 2) ? a.cz : A.Sz;
+        facing = __fadd_rn(__fadd_rn(__fmul_rn(rx, nx), __fmul_rn(ry, ny)), __fmul_rn(rz, nz));
+    }
+    float2* o = reinterpret_cast<float2*>(p6 + gid * 6);
+    o[0] = make_float2(a.px, a.py); o[1] = make_float2(bb.px, bb.py); o[2] = make_float2(c.px, c.py);
+    len3[gid * 3 + 0] = a.len; len3[gid * 3 + 1] = bb.len; len3[gid * 3 + 2] = c.len;
+    ff[gid] = facing;
+}
+
+// cotangent of one vertex: (gpx, gpy, glen) -> d/d(x,y,z), hand-written reverse mode of
+// project_vertex (== what torch autograd does through fp_opengl.py:87-158 / fp_vecs.py:101-173)
+__device__ __forceinline__ void vertex_vjp(const VertexParams& P, const AngleConst& A,
+                                           float x, float y, float z, float gpx, float gpy, float glen,
+                                           float& gx, float& gy, float& gz) {
+    const VertexOut o = project_vertex(P, A, x, y, z);
+    if (P.kind == 0) {
+        const float il = 1.0f / o.len;
+        const float gxr = gpx * (0.5f * (float)P.W * P.P00) + glen * o.cx * il;
+        const float gcy = gpy * (-0.5f * (float)P.H * P.P11) + glen * o.cy * il;   // cam y = -z
+        const float gyr = glen * o.cz * il;
+        gx = gxr * A.ct - gyr * A.st;
+        gy = gxr * A.st + gyr * A.ct;
+        gz = -gcy;
+        return;
+    }
+    // P = base + t*r ; px = (P - DetS).{x|y} / u.{x|y} ; py = (P - DetS).z / vz
+    float gPx = 0.0f, gPy = 0.0f;
+    if (A.use_x) gPx = gpx / A.ux; else gPy = gpx / A.uy;
+    const float gPz = gpy / A.vz;
+    if (P.kind == 1) {
+        // base = v, r = -S (constant), t = -(N.v + msv)/NR, len = t
+        const float NR = A.N0 * o.cx + A.N1 * o.cy;
+        const float gt = gPx * o.cx + gPy * o.cy + gPz * o.cz + glen;
+        const float gNS = -gt / NR;
+        gx = gPx + gNS * A.N0;
+        gy = gPy + gNS * A.N1;
+        gz = gPz;
+        return;
+    }
+    // cone: R = v - S, len = |R|, r = R/len, t = coeff/(N.r_xy + 1e-10), P = S + t*r
+    const float NRe = A.N0 * o.cx + A.N1 * o.cy + 1e-10f;
+    const float gt = gPx * o.cx + gPy * o.cy + gPz * o.cz;
+    float grx = o.t * gPx, gry = o.t * gPy, grz = o.t * gPz;
+    const float gNR = -gt * o.t / NRe;
+    grx += gNR * A.N0; gry += gNR * A.N1;
+    const float il = 1.0f / o.len;
+    const float rdot = o.cx * grx + o.cy * gry + o.cz * grz;
+    gx = (grx - o.cx * rdot) * il + glen * o.cx;
+    gy = (gry - o.cy * rdot) * il + glen * o.cy;
+    gz = (grz - o.cz * rdot) * il + glen * o.cz;
+}
+
+// thread per face, angle slices along grid.y: sums the cotangents of the face's three corners over
+// the slice's angles in registers, then one atomic per (slice, corner, axis)
+__global__ void __launch_bounds__(256)
+k_vertex_backward(const VertexParams P, const float* __restrict__ grad_p6,
+                  const float* __restrict__ grad_len3, float* __restrict__ grad_verts, int angles_per_slice) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P.F) return;
+    const int b0 = blockIdx.y * angles_per_slice, b1 = min(b0 + angles_per_slice, P.B);
+    const int vi[3] = {__ldg(P.faces + 3 * f), __ldg(P.faces + 3 * f + 1), __ldg(P.faces + 3 * f + 2)};
+    float vx[3], vy[3], vz[3], ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        vx[k] = __ldg(P.verts + 3 * vi[k]); vy[k] = __ldg(P.verts + 3 * vi[k] + 1); vz[k] = __ldg(P.verts + 3 * vi[k] + 2);
+    }
+    bool any = false;
+    for (int b = b0; b < b1; ++b) {
+        const long long bf = (long long)b * P.F + f;
+        const float2* gp = reinterpret_cast<const float2*>(grad_p6 + bf * 6);
+        const float2 g0 = __ldg(gp), g1 = __ldg(gp + 1), g2 = __ldg(gp + 2);
+        const float l0 = __ldg(grad_len3 + bf * 3), l1 = __ldg(grad_len3 + bf * 3 + 1), l2 = __ldg(grad_len3 + bf * 3 + 2);
+        if (g0.x == 0.f && g0.y == 0.f && g1.x == 0.f && g1.y == 0.f && g2.x == 0.f && g2.y == 0.f &&
+            l0 == 0.f && l1 == 0.f && l2 == 0.f) continue;
+        any = true;
+        const AngleConst A = angle_const(P, b);
+        const float gpx[3] = {g0.x, g1.x, g2.x}, gpy[3] = {g0.y, g1.y, g2.y}, gl[3] = {l0, l1, l2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float gx, gy, gz;
+            vertex_vjp(P, A, vx[k], vy[k], vz[k], gpx[k], gpy[k], gl[k], gx, gy, gz);
+            ax[k] += gx; ay[k] += gy; az[k] += gz;
+        }
+    }
+    if (!any) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        atomicAdd(grad_verts + 3 * vi[k] + 0, ax[k]);
+        atomicAdd(grad_verts + 3 * vi[k] + 1, ay[k]);
+        atomicAdd(grad_verts + 3 * vi[k] + 2, az[k]);
+    }
+}
+
+}  // namespace ctdr
