@@ -109,7 +109,7 @@ k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
     int ix0, iy0, ix1, iy1;
     if (!face_int_bbox(va.x, va.y, vb.x, vb.y, vc.x, vc.y, P.H, P.W, ix0, iy0, ix1, iy1)) return;
     const EdgeSetup es = edge_setup(va.x, va.y, vb.x, vb.y, vc.x, vc.y);
-    float M0 = 0.0f, Ms = 0.0f, Mt = 0.0f;
+    float M0 = 0.0f, Ms = 0.0f, Mt = 0.0f, A1 = 0.0f, A2 = 0.0f;
     const long long base = (long long)b * P.H * P.W;
     for (int y = iy0; y <= iy1; ++y)
         for (int x = ix0; x <= ix1; ++x) {
@@ -118,17 +118,17 @@ k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
             if (g == 0.0f) continue;
             const float v = __ldg(P.im_in + o);
             if (((double)v < -1e-5) || (v > P.msv)) continue;              // diff_fp_for.cu:69-73
-            float s, t, w0, w1, w2;
-            if (!cover_exact<PREFILTER>(es, (float)x, (float)y, s, t, w0, w1, w2)) continue;
-            M0 += g; Ms += g * s; Mt += g * t;
+            float s, t, k1, k2, w0, w1, w2;
+            if (!cover_exact<PREFILTER>(es, (float)x, (float)y, s, t, k1, k2, w0, w1, w2)) continue;
+            M0 += g; Ms += g * s; Mt += g * t; A1 += g * k1; A2 += g * k2;
         }
-    if (M0 == 0.0f && Ms == 0.0f && Mt == 0.0f) return;
+    if (M0 == 0.0f && Ms == 0.0f && Mt == 0.0f && A1 == 0.0f && A2 == 0.0f) return;
     float sgn = (__ldg(P.ff + gid) < 0.0f) ? -1.0f : 1.0f;
     if (lab.x == lab.y) sgn = -sgn;
     const float r0 = __ldg(P.len3 + gid * 3), r1 = __ldg(P.len3 + gid * 3 + 1), r2 = __ldg(P.len3 + gid * 3 + 2);
     const float cgeo = sgn * (__ldg(P.mus + lab.x) - __ldg(P.mus + lab.y));
     float gp[6], gl[3], bsum;
-    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, gp, gl, bsum);
+    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, A1, A2, gp, gl, bsum);
 #pragma unroll
     for (int k = 0; k < 6; ++k) P.grad_p6[gid * 6 + k] += gp[k];
 #pragma unroll

@@ -70,11 +70,12 @@ __device__ __forceinline__ EdgeSetup edge_setup(float ax, float ay, float bx, fl
 // identical with and without the prefilter.
 template <bool PREFILTER>
 __device__ __forceinline__ bool cover_exact(const EdgeSetup& e, float x0, float y0,
-                                            float& s, float& t, float& w0, float& w1, float& w2) {
+                                            float& s, float& t, float& k1, float& k2,
+                                            float& w0, float& w1, float& w2) {
     s = __fsub_rn(x0, e.ax);
     t = __fsub_rn(y0, e.ay);
-    const float k1 = __fmaf_rn(s, e.q, -__fmul_rn(e.n, t));
-    const float k2 = __fmaf_rn(e.m, t, -__fmul_rn(s, e.p));
+    k1 = __fmaf_rn(s, e.q, -__fmul_rn(e.n, t));
+    k2 = __fmaf_rn(e.m, t, -__fmul_rn(s, e.p));
     const double d = (double)e.k3 + 1e-15;
     if (PREFILTER) {
         // |k3| in (1e-6, 1e10): d = k3 + 1e-15 has the sign of k3 and 1/k3 approximates 1/d to 1e-9.

@@ -96,7 +96,7 @@ struct __align__(16) WarpSmem {
     int   box[32];               // lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13
     int   excl[32];              // exclusive candidate offset of the slot
     int   offs[32];              // inclusive candidate offsets (binary-searched)
-    float mom[3][32];            // backward: sum g, sum g*s, sum g*t per slot
+    float mom[5][32];            // backward: sum g, g*s, g*t, g*k1, g*k2 per slot
     // tile accumulators
     float acc[TILE_PIX];         // forward: running sinogram; backward: g (0 where no gradient)
     int   cntv[TILE_PIX];        // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel
@@ -117,29 +117,33 @@ __device__ __forceinline__ bool box_overlap(const short4 bx, int x0, int y0, int
 }
 
 // segmented (by contiguous key) reduction toward the lowest lane of each run
-__device__ __forceinline__ void seg_reduce3(int key, int lane, float& a, float& b, float& c) {
+__device__ __forceinline__ void seg_reduce5(int key, int lane, float (&v)[5]) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const int   k2 = __shfl_down_sync(FULL, key, d);
-        const float a2 = __shfl_down_sync(FULL, a, d);
-        const float b2 = __shfl_down_sync(FULL, b, d);
-        const float c2 = __shfl_down_sync(FULL, c, d);
-        if (lane + d < 32 && k2 == key) { a += a2; b += b2; c += c2; }
+        const int kk = __shfl_down_sync(FULL, key, d);
+        float u[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) u[k] = __shfl_down_sync(FULL, v[k], d);
+        if (lane + d < 32 && kk == key) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] += u[k];
+        }
     }
 }
 
 
-// Gradients of one face from the moments M0 = sum g, Ms = sum g*s, Mt = sum g*t of the upstream
-// gradient over the face's fragments (s = x0-ax, t = y0-ay).  k1 = s*q - n*t and k2 = m*t - s*p are
-// linear in (s,t), so the per-fragment sums of diff_fp_back.cu:126-136 (grad_len),
-// :143-147 (sum of interpolated length * g, for grad_mus) and :206-292 (grad_points2d) close in
-// these three numbers.  cgeo = sign*(mu_in - mu_out): the two label iterations of back.cu:111 merged.
+// Gradients of one face from five moments of the upstream gradient g over the face's fragments:
+// M0 = sum g, Ms = sum g*s, Mt = sum g*t, A1 = sum g*k1, A2 = sum g*k2 (s = x0-ax, t = y0-ay, k1/k2
+// exactly as the forward computes them).  Every per-fragment term of diff_fp_back.cu:126-136
+// (grad_len), :143-147 (interpolated length * g, for grad_mus) and :206-292 (grad_points2d) is a
+// per-face constant times one of {1, s, t, k1, k2}, and s,t only ever appear multiplied by k3 — so
+// a zero-area face (k1 = k2 = k3 = 0) yields exact zeros like the reference, before the 1/(k3^2+eps)
+// factor.  cgeo = sign*(mu_in - mu_out): the two label iterations of back.cu:111 merged.
 __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, float r0, float r1, float r2,
                                                         float cgeo, float M0, float Ms, float Mt,
+                                                        float A1, float A2,
                                                         float gp[6], float gl[3], float& bsum) {
     const float k3 = es.k3;
-    const float A1 = es.q * Ms - es.n * Mt;                   // sum g*k1
-    const float A2 = es.m * Mt - es.p * Ms;                   // sum g*k2
     const double dd = (double)k3 + 1e-15;
     const float W1 = (float)((double)A1 / dd), W2 = (float)((double)A2 / dd);
     const float W0 = M0 - W1 - W2;                            // sum g*w_k
@@ -228,7 +232,10 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
             S.cA[lane] = __fmul_rn(sgn, mu_in);                       // :187
             S.cB[lane] = -__fmul_rn(sgn, mu_out);                     // :190
         }
-        if (IS_BWD) { S.mom[0][lane] = 0.0f; S.mom[1][lane] = 0.0f; S.mom[2][lane] = 0.0f; }
+        if (IS_BWD) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) S.mom[k][lane] = 0.0f;
+        }
     }
     __syncwarp();
 
@@ -251,8 +258,8 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         const int pl = py * TILE + px;
         EdgeSetup c;
         c.ax = S.ax[i]; c.ay = S.ay[i]; c.m = S.m[i]; c.p = S.p[i]; c.n = S.n[i]; c.q = S.q[i]; c.k3 = S.k3[i];
-        float s, t, w0, w1, w2;
-        bool in = cover_exact<PREFILTER>(c, (float)(tx0 + px), (float)(ty0 + py), s, t, w0, w1, w2);
+        float s, t, k1, k2, w0, w1, w2;
+        bool in = cover_exact<PREFILTER>(c, (float)(tx0 + px), (float)(ty0 + py), s, t, k1, k2, w0, w1, w2);
         in = in && act;
         if (act) st.cand++;
 
@@ -309,12 +316,13 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         } else {  // backward: per-face moments of the upstream gradient
             float g = 0.0f;
             if (in) { g = S.acc[pl]; if (g != 0.0f) st.frag++; }
-            float g0 = g, gs = g * s, gt = g * t;
+            float v[5] = {g, g * s, g * t, g * k1, g * k2};
             if (__ballot_sync(FULL, g != 0.0f)) {
-                seg_reduce3(i, lane, g0, gs, gt);
+                seg_reduce5(i, lane, v);
                 const int iprev = __shfl_up_sync(FULL, i, 1);
                 if (lane == 0 || iprev != i) {        // run head: distinct slots, no conflicts
-                    S.mom[0][i] += g0; S.mom[1][i] += gs; S.mom[2][i] += gt;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) S.mom[k][i] += v[k];
                 }
                 __syncwarp();
             }
@@ -322,15 +330,14 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
     }
 
     if (IS_BWD && ncand > 0) {
-        // Per-face gradients from the moments M0 = sum g, Ms = sum g*s, Mt = sum g*t over the face's
-        // fragments in this tile.  k1 = s*q - n*t and k2 = m*t - s*p are linear in (s,t), so the sums
-        // of diff_fp_back.cu:231-292 over fragments close in (M0, Ms, Mt); see DESIGN.md.
+        // per-face gradients from the five moments of this tile's fragments (face_grads_from_moments)
         const float M0 = S.mom[0][lane], Ms = S.mom[1][lane], Mt = S.mom[2][lane];
-        if (M0 != 0.0f || Ms != 0.0f || Mt != 0.0f) {
+        const float A1 = S.mom[3][lane], A2 = S.mom[4][lane];
+        if (M0 != 0.0f || Ms != 0.0f || Mt != 0.0f || A1 != 0.0f || A2 != 0.0f) {
             const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
             const float cgeo = sgn * (mu_in - mu_out);                // raw mu, no label-0 flip (back.cu:115)
             float gp[6], gl[3], bsum;
-            face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, gp, gl, bsum);
+            face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, A1, A2, gp, gl, bsum);
             float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
             atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
             // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
