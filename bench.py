@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd detector Gpix/s of the mesh projector (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
+
+One "step" = one projection + masked-L2 residual + backward sweep over ALL angles of the workload
+(angles sharded over the N ranks, mesh replicated) followed by the all-reduce of the gradients —
+the data-path of one optimiser iteration (ctdr/optimize.py:162-190).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd detector Gpix/s"
+CPU_SAMPLE = dict(angles=2, rows=32)          # bounded sample of the workload for the CPU arm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (oracle port; the extension has no CPU path)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, repeats=1):
+    """Time vertex stage + Rasterizer forward (pass 1 + pass 2) + backward of the reference
+    algorithm (pixel-parallel, loop over all faces) on CPU_SAMPLE of the workload."""
+    from oracle import oracle, vertex_stage
+    na, rows = CPU_SAMPLE["angles"], CPU_SAMPLE["rows"]
+    H, W = wl["H"], wl["W"]
+    na = min(na, wl["nangles"]); rows = min(rows, H)
+    idx = np.linspace(0, wl["nangles"], na, endpoint=False).astype(np.int64)
+    y0 = (H - rows) // 2
+    oracle.lib()
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        geom = wl["geom"]
+        full_idx = np.arange(wl["nangles"])
+        if geom["type"][-3:] == "vec":      # fp_vecs needs the full angle set; project only the sample
+            sub = dict(geom, Vectors=geom["Vectors"][idx])
+            p6, len3, ff, msv = vertex_stage.vertex_stage(sub, wl["verts"], wl["faces"], np.arange(na), np.float32)
+        else:
+            p6, len3, ff, msv = vertex_stage.vertex_stage(geom, wl["verts"], wl["faces"], full_idx[idx], np.float32)
+        bb = oracle.bbox(p6)
+        im = np.zeros((na, H, W, 1), np.float32); cnt = np.zeros((na, H, W, 1), np.int32)
+        oracle.forward_pass(p6, ff, bb, len3, wl["labels"], wl["mus"], None, None, cnt, None, im, 1, msv,
+                            rows=(y0, y0 + rows))
+        cumsum = np.cumsum(cnt.reshape(-1), dtype=np.int32)
+        vf = int(cumsum[-1])
+        imwei = np.zeros(3 * vf, np.float32); imidx = np.zeros(vf, np.int32)
+        first = np.zeros(na * H * W, np.int32); first[1:] = cumsum[:-1]
+        first = first.reshape(na, H, W, 1)
+        oracle.forward_pass(p6, ff, bb, len3, wl["labels"], wl["mus"], imwei, imidx, cnt, first, im, 0, msv,
+                            rows=(y0, y0 + rows))
+        g = np.ones_like(im)
+        fwd = dict(im=im, cnt=cnt, firstidx=first, imidx=imidx, imwei=imwei)
+        oracle.rasterizer_backward(g, fwd, p6, len3, ff, wl["labels"], wl["mus"], rows=(y0, y0 + rows))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    pixels = na * rows * W
+    return pixels / best / 1e9, best, f"{na} angles x {rows} detector rows x {W} cols x full mesh ({wl['faces'].shape[0]} faces)"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from shapefromprojections_b200 import workloads
+    wl = workloads.make_workload(args.config)
+    cores = os.cpu_count()
+    times = []
+    for i in range(args.warmup + args.steps):
+        gpix, dt, sample = cpu_reference_sample(wl)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    pixels = min(CPU_SAMPLE["angles"], wl["nangles"]) * min(CPU_SAMPLE["rows"], wl["H"]) * wl["W"]
+    value = pixels / (ms / 1e3) / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {wl['desc']}; reference algorithm on host cores, each step = "
+                                   f"a bounded sample ({sample}); pixels are independent in that algorithm"},
+            "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from shapefromprojections_b200 import _lib, distributed, workloads
+    from shapefromprojections_b200.function import rasterizer as R
+
+    rank, world, local_rank = distributed.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.lib()
+
+    wl = workloads.make_workload(args.config)
+    H, W, NA = wl["H"], wl["W"], wl["nangles"]
+    V, F = wl["verts"].shape[0], wl["faces"].shape[0]
+    b0, b1 = distributed.shard_angles(NA, rank, world)
+    Bl = b1 - b0
+    gd = R.GeometryDevice(wl["geom"], dev)
+    verts = torch.as_tensor(wl["verts"]).to(dev)
+    faces32 = torch.as_tensor(wl["faces"]).to(torch.int32).to(dev)
+    labels = torch.as_tensor(wl["labels"]).to(dev)
+    mus = torch.as_tensor(wl["mus"]).to(dev)
+    idx = torch.arange(b0, b1, device=dev, dtype=torch.int64)
+
+    # seeded target: projection of the ground-truth shape (the mesh scaled anisotropically)
+    gt = verts * torch.as_tensor(workloads.TARGET_SCALE).to(dev)
+    target, _, _ = R.project_forward(gd, gt, faces32, labels, mus, idx)
+    phat = torch.empty_like(target)
+    xch = distributed.GradientExchange(V, mus.numel(), dev)
+    stats = None
+
+    def step():
+        xch.zero_()
+        R.project_residual_step(gd, verts, faces32, labels, mus, idx, target, phat=phat,
+                                grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
+        xch.all_reduce()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    pixels = NA * H * W
+    value = pixels / (ms_step / 1e3) / 1e9
+    loss_sum, n_valid = (float(x) for x in xch.scalars.tolist())
+
+    # ---- end to end: host buffers in, host results out, every step -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_verts = wl_pin(torch, wl["verts"]); h_mus = wl_pin(torch, wl["mus"])
+        h_idx = torch.arange(b0, b1, dtype=torch.int64).pin_memory()
+        h_target = torch.empty(target.shape, dtype=torch.float32).pin_memory()
+        h_target.copy_(target)
+        h_grad = torch.empty(xch.flat.shape, dtype=torch.float32).pin_memory()
+        h_scal = torch.empty(2, dtype=torch.float64).pin_memory()
+        d_target = torch.empty_like(target)
+
+        def e2e_step():
+            v = h_verts.to(dev, non_blocking=True); m = h_mus.to(dev, non_blocking=True)
+            ix = h_idx.to(dev, non_blocking=True)
+            d_target.copy_(h_target, non_blocking=True)
+            xch.zero_()
+            R.project_residual_step(gd, v, faces32, labels, m, ix, d_target, phat=phat,
+                                    grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
+            xch.all_reduce()
+            h_grad.copy_(xch.flat, non_blocking=True)
+            h_scal.copy_(xch.scalars, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # the caller reads loss and gradients on the host
+
+        n_e2e = max(2, min(args.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ms = 1e3 * float(dt.item()) / n_e2e
+        h2d = world_sum(torch, dist, world, dev, h_target.numel() * 4 + h_verts.numel() * 4 + h_mus.numel() * 4 + h_idx.numel() * 8)
+        d2h = world_sum(torch, dist, world, dev, h_grad.numel() * 4 + 16)
+        e2e = {"value": pixels / (e2e_ms / 1e3) / 1e9, "unit": "Gpix/s", "ms_per_step": e2e_ms, "steps": n_e2e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "what": "pinned host verts/mus/idx_angles/target -> device, fused step, all-reduce, gradients + loss -> host"}
+        del h_target, d_target
+
+    # ---- per-kernel breakdown (staged entry points, CUDA events on the launching stream) ----------
+    breakdown = None
+    if not args.no_breakdown and rank == 0:
+        breakdown = kernel_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, phat)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    alg_bytes = workloads.algorithmic_bytes(NA, H, W, V, F, world)
+    achieved = alg_bytes / (ms_step / 1e3) / 1e9 / world          # GB/s per GPU
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "what": "algorithmic bytes of one step (8 B/pixel + mesh term) / step time, per GPU; "
+                        "dominant kernels listed in `kernels`"}
+    line = {"metric": METRIC, "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {wl['desc']}", "angles_per_gpu": Bl, "V": V, "F": F,
+                       "step": "projection + masked-L2 residual + backward over all angles + gradient all-reduce",
+                       "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)",
+                       "parallelism": f"angles sharded over {world} GPU(s), mesh replicated"},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "loss": loss_sum / max(n_valid, 1.0), "n_valid": n_valid}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if breakdown is not None:
+        line["kernels"] = breakdown
+        if "raster_step_ms" in breakdown:
+            k_bytes = 8 * Bl * H * W      # read phat + read target (the kernel's own algorithmic bytes)
+            line["roofline"]["dominant_kernel"] = {
+                "name": "k_raster<MODE_STEP>", "ms": breakdown["raster_step_ms"],
+                "achieved": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9, "unit": "GB/s",
+                "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak}
+    if not args.no_cpu_baseline and world == 1:
+        gpix, dt, sample = cpu_reference_sample(wl)
+        line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": sample, "seconds": dt}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+LAUNCHES_PER_STEP = 7   # forward: vertex, chunk-bbox, raster; backward sweep: vertex, chunk-bbox, raster-step, vertex-bwd
+
+
+def wl_pin(torch, arr):
+    return torch.as_tensor(np.ascontiguousarray(arr)).pin_memory()
+
+
+def world_sum(torch, dist, world, dev, v):
+    t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t)
+    return int(t.item())
+
+
+def kernel_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, phat, reps=3):
+    """Time the stages of one step through the staged C-ABI entry points (same kernels)."""
+    from shapefromprojections_b200 import _lib
+    out = {}
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    try:
+        p6, len3, ff = R.vertex_forward(gd, verts, faces32, idx)
+        out["vertex_forward_ms"] = timed(lambda: R.vertex_forward(gd, verts, faces32, idx))
+        out["raster_forward_ms"] = timed(lambda: R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val))
+        im, _, st = R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val, want_stats=True)
+        g = (2.0 * (im.squeeze(-1) - target)).unsqueeze(-1).contiguous()
+        out["raster_backward_ms"] = timed(lambda: R.raster_backward(g, im, p6, len3, ff, labels, mus, gd.max_sino_val))
+        out["raster_step_ms"] = out["raster_backward_ms"]
+        st = st.tolist()
+        out["fragments"] = st[_lib.STAT_FRAGMENTS]; out["candidates"] = st[_lib.STAT_CANDIDATES]
+        out["nonpositive_len"] = st[_lib.STAT_NONPOSITIVE_LEN]; out["list_segments"] = st[_lib.STAT_LIST_SEGMENTS]
+        out["full_forward_ms"] = timed(lambda: R.project_forward(gd, verts, faces32, labels, mus, idx))
+    except torch.cuda.OutOfMemoryError:
+        out["note"] = "staged breakdown skipped (out of memory)"
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,65 @@
+"""Angle-sharded data parallelism: the only multi-GPU strategy of this path.
+
+Every projection angle is independent (``fp_vecs.py:101``, ``fp_opengl.py:89-90``), so rank ``r`` owns a
+contiguous block of ``idx_angles``; the mesh is replicated; sinogram / target shards never leave
+their GPU.  The one exchange per optimiser iteration is an all-reduce (SUM) of the vertex and
+attenuation gradients plus the two loss scalars.  The reference has no distributed code at all.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's environment; single process when unset."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local_rank
+
+
+def shard_angles(nangles: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block [begin, end) of rank ``rank``; block sizes differ by at most one angle."""
+    base, rem = divmod(nangles, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class GradientExchange:
+    """Flat, pre-allocated all-reduce buffers the backward writes into directly (no pack kernel).
+
+    ``flat`` (fp32) = [grad_verts (3V) | grad_mus (n)], ``scalars`` (fp64) = [loss_sum, n_valid].
+    """
+
+    def __init__(self, num_verts: int, num_mus: int, device):
+        self.flat = torch.zeros(3 * num_verts + num_mus, dtype=torch.float32, device=device)
+        self.grad_verts = self.flat[:3 * num_verts].view(num_verts, 3)
+        self.grad_mus = self.flat[3 * num_verts:]
+        self.scalars = torch.zeros(2, dtype=torch.float64, device=device)
+
+    def zero_(self):
+        self.flat.zero_()
+        self.scalars.zero_()
+
+    def all_reduce(self):
+        """Sum over ranks, enqueued on the current stream right behind the backward kernels."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.scalars, op=dist.ReduceOp.SUM)
+
+    def mean_gradients(self):
+        """d(mean over valid pixels)/d(verts, mus) and the mean loss, from the all-reduced sums."""
+        n = self.scalars[1].clamp(min=1.0)
+        inv = (1.0 / n).to(torch.float32)
+        return self.grad_verts * inv, self.grad_mus * inv, self.scalars[0] / n

@@ -1,0 +1,176 @@
+"""GPU tests of the vertex stage and the fused projector (mesh + geometry in, sinogram out)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import oracle, vertex_stage
+from test_gpu_raster import bits, dev
+from test_oracle_golden import _geom_from_npz
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+GEOMS = {
+    "parallel3d": lambda: cases.parallel_geometry(6, 160),
+    "parallel3d_vec": lambda: __import__("shapefromprojections_b200.utils.util_sino", fromlist=["x"]).geom_2vec(cases.parallel_geometry(6, 160)),
+    "cone_vec": lambda: cases.cone_geometry(6, 160),
+}
+
+
+def setup(geom, mesh):
+    from shapefromprojections_b200.function import rasterizer as R
+    verts, faces, labels, mus = mesh
+    g = R.GeometryDevice(geom, "cuda")
+    return g, dev(verts), dev(faces, torch.int32), dev(labels), dev(mus)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "vertex_stage_*_f32.npz"))))
+def test_vertex_forward_vs_reference_modules(cuda_lib, path):
+    """Device vertex stage vs what the reference's FP modules hand to Rasterizer.apply (golden, torch CPU)."""
+    from shapefromprojections_b200.function import rasterizer as R
+    g = np.load(path)
+    geom = _geom_from_npz(g)
+    gd = R.GeometryDevice(geom, "cuda")
+    assert gd.max_sino_val == g["msv"]
+    p6, len3, ff = R.vertex_forward(gd, dev(g["verts"], torch.float32), dev(g["faces"], torch.int32), g["idx_angles"])
+    torch.cuda.synchronize()
+    tol_px = 1e-3 if geom["type"] == "cone_vec" else 1e-4        # float32 op-order noise
+    assert np.abs(p6.cpu().numpy() - g["p6"]).max() <= tol_px
+    assert np.abs(len3.cpu().numpy() - g["len3"]).max() <= 5e-6
+    big = np.abs(g["ff"]) > 1e-6
+    assert np.array_equal((ff.cpu().numpy() < 0)[big], (g["ff"] < 0)[big])
+
+
+@pytest.mark.parametrize("kind", list(GEOMS))
+def test_vertex_backward_is_transposed_jacobian(cuda_lib, kind):
+    """<J^T g, d> == d/d eps <g, f(v + eps d)> with f evaluated in float64 by the NumPy restatement."""
+    from shapefromprojections_b200.function import rasterizer as R
+    geom = GEOMS[kind]()
+    verts, faces, labels, mus = cases.two_material_mesh(1)
+    gd, v, f32, _, _ = setup(geom, (verts, faces, labels, mus))
+    idx = np.arange(6)
+    rng = np.random.default_rng(0)
+    B, F = 6, faces.shape[0]
+    gp6 = rng.normal(size=(B, F, 6)).astype(np.float32)
+    gl3 = rng.normal(size=(B, F, 3)).astype(np.float32)
+    vreq = v.clone().requires_grad_(True)
+    p6, len3, ff = R.VertexStage.apply(vreq, f32, idx, gd)
+    ((p6 * dev(gp6)).sum() + (len3 * dev(gl3)).sum()).backward()
+    gv = vreq.grad.cpu().numpy().astype(np.float64)
+
+    def phi(vv):
+        a, b, _, _ = vertex_stage.vertex_stage(geom, vv, faces, idx, np.float64)
+        return (a * gp6).sum() + (b * gl3).sum()
+    for k in range(3):
+        d = rng.normal(size=verts.shape)
+        eps = 1e-6
+        fd = (phi(verts.astype(np.float64) + eps * d) - phi(verts.astype(np.float64) - eps * d)) / (2 * eps)
+        an = (gv * d).sum()
+        assert abs(fd - an) <= 2e-4 * max(abs(fd), 1.0), (kind, fd, an)
+
+
+@pytest.mark.parametrize("kind", list(GEOMS))
+def test_fused_forward_equals_staged_and_oracle(cuda_lib, kind):
+    from shapefromprojections_b200.function import rasterizer as R
+    geom = GEOMS[kind]()
+    mesh = cases.two_material_mesh(2)
+    gd, v, f32, labels, mus = setup(geom, mesh)
+    idx = torch.arange(6, device="cuda")
+    im, cnt, stats = R.project_forward(gd, v, f32, labels, mus, idx, want_cnt=True, want_stats=True)
+    p6, len3, ff = R.vertex_forward(gd, v, f32, idx)
+    im2, cnt2, _ = R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val, want_cnt=True)
+    torch.cuda.synchronize()
+    assert torch.equal(cnt, cnt2.squeeze(-1)) and torch.equal(im, im2.squeeze(-1))     # same kernels: bit-exact
+    # the staged tensors through the CPU oracle: bit-exact again (identical p6 -> identical coverage)
+    o = oracle.rasterizer_forward(p6.cpu().numpy(), len3.cpu().numpy(), ff.cpu().numpy(), mesh[2], mesh[3],
+                                  gd.H, gd.W, gd.max_sino_val, False, fast=True)
+    assert np.array_equal(cnt.cpu().numpy(), o["cnt"][..., 0])
+    assert np.array_equal(bits(im.cpu().numpy()), bits(o["im"][..., 0]))
+    # against the NumPy vertex stage (different op chain): only knife-edge pixels may differ
+    q6, l3, f1, msv = vertex_stage.vertex_stage(geom, mesh[0], mesh[1], np.arange(6), np.float32)
+    o2 = oracle.rasterizer_forward(q6, l3, f1, mesh[2], mesh[3], gd.H, gd.W, msv, False, fast=True)
+    diff = cnt.cpu().numpy() != o2["cnt"][..., 0]
+    assert diff.mean() < 2e-4, f"{diff.sum()} coverage mismatches"
+    same = ~diff
+    a, b = im.cpu().numpy()[same], o2["im"][..., 0][same]
+    depth = max(int(o2["cnt"].max()), 1)
+    tol = 1e-5 * np.abs(b) + 4 * depth * np.spacing(np.float32(l3.max())) * np.abs(mesh[3]).max() + 1e-4 * (kind == "cone_vec")
+    assert (np.abs(a - b) <= tol).all(), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("kind", list(GEOMS))
+def test_fused_backward_equals_staged_autograd(cuda_lib, kind):
+    from shapefromprojections_b200.function import rasterizer as R
+    geom = GEOMS[kind]()
+    mesh = cases.two_material_mesh(2)
+    gd, v, f32, labels, mus = setup(geom, mesh)
+    idx = torch.arange(6, device="cuda")
+    w = torch.randn(6, gd.H, gd.W, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    v1 = v.clone().requires_grad_(True); m1 = mus.clone().requires_grad_(True)
+    im = R.ProjectMesh.apply(v1, m1, f32, labels, idx, gd, True)
+    (im * w).sum().backward()
+    v2 = v.clone().requires_grad_(True); m2 = mus.clone().requires_grad_(True)
+    p6, len3, ff = R.VertexStage.apply(v2, f32, idx, gd)
+    im2 = R.Rasterizer.apply(p6, len3, ff, labels, m2, gd.H, gd.W, gd.max_sino_val, True)
+    (im2.squeeze(-1) * w).sum().backward()
+    torch.cuda.synchronize()
+    for a, b in ((v1.grad, v2.grad), (m1.grad, m2.grad)):
+        assert (a - b).norm() <= 1e-5 * b.norm() + 1e-12, ((a - b).norm().item(), b.norm().item())
+    assert v1.grad.abs().max() > 0
+
+
+def test_residual_step_matches_autograd_of_masked_l2(cuda_lib):
+    """ctdr/optimize.py:162-168: loss = mean over valid of (p - phat)^2, through the fused step."""
+    from shapefromprojections_b200.function import rasterizer as R
+    from shapefromprojections_b200.nn.fp_vecs import get_valid_mask
+    geom = GEOMS["parallel3d"]()
+    mesh = cases.two_material_mesh(2)
+    gd, v, f32, labels, mus = setup(geom, mesh)
+    idx = torch.arange(6, device="cuda")
+    target = torch.rand(6, gd.H, gd.W, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    phat, gv, gm, out2 = R.project_residual_step(gd, v, f32, labels, mus, idx, target)
+    v1 = v.clone().requires_grad_(True); m1 = mus.clone().requires_grad_(True)
+    im = R.ProjectMesh.apply(v1, m1, f32, labels, idx, gd, True)
+    mask = get_valid_mask(im, gd.max_sino_val)
+    loss = (target - im)[mask].pow(2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(phat, im.detach())
+    n_valid = int(mask.sum())
+    assert int(out2[1].item()) == n_valid
+    assert abs(out2[0].item() / n_valid - loss.item()) <= 1e-5 * loss.item()
+    assert (gv / n_valid - v1.grad).norm() <= 2e-5 * v1.grad.norm()
+    assert (gm / n_valid - m1.grad).norm() <= 2e-5 * m1.grad.norm()
+
+
+@pytest.mark.parametrize("kind", list(GEOMS))
+def test_fp_modules_surface(cuda_lib, kind):
+    """FP(proj_geom, labels, dtype).forward(verts, faces, idx_angles, mus, backprop) -> (phat, mask_valid)."""
+    geom = GEOMS[kind]()
+    verts, faces, labels, mus = cases.two_material_mesh(1)
+    if kind == "parallel3d":
+        from shapefromprojections_b200.nn.fp_opengl import FP
+    else:
+        from shapefromprojections_b200.nn.fp_vecs import FP
+    lab = torch.as_tensor(labels)
+    fp = FP(geom, lab, torch.float32)
+    fp_staged = FP(geom, lab, torch.float32, fused=False)
+    v = dev(verts).requires_grad_(True); m = dev(mus).requires_grad_(True)
+    faces64 = dev(faces)                                 # int64, as Model registers it (vanilla.py:47)
+    idx_cpu = torch.arange(6)                            # the reference passes a CPU LongTensor (optimize.py:125)
+    phat, mask = fp.forward(v, faces64, idx_cpu, m)
+    phat2, mask2 = fp_staged.forward(v, faces64, idx_cpu, m)
+    assert phat.shape == (6, fp.height, fp.width) and mask.dtype == torch.bool
+    assert torch.equal(phat, phat2) and torch.equal(mask, mask2)
+    assert fp_staged.proj.shape == (6, faces.shape[0], 6) and fp_staged.len.shape == (6, faces.shape[0], 3)
+    phat.sum().backward()
+    assert v.grad is not None and m.grad is not None
+    one, _ = fp.forward(v, faces64, torch.tensor([2]), m, backprop=False)
+    assert one.shape == (fp.height, fp.width)            # phat.squeeze() drops B == 1 (fp_vecs.py:203)
+    assert torch.equal(one, phat[2].detach())
+    with pytest.raises(TypeError):
+        FP(geom, lab, torch.float64)
