@@ -67,6 +67,13 @@ typedef struct CUstream_st* ctdr_stream_t;   /* == cudaStream_t */
 int         ctdr_abi_version(void);
 const char* ctdr_last_error(void);
 
+/* Self-test of the one arithmetic shortcut the kernels take: fl32(k1/(k3+1e-15)) through the
+ * per-face reciprocal + one fused correction step vs the IEEE fp64 division of the reference
+ * (diff_fp_for.cu:144-145), over `samples` pseudo-random float pairs.  *mismatches (device uint64,
+ * caller zeroes it) receives the number of bitwise differences; it must stay 0. */
+int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned long long* mismatches,
+                           ctdr_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Rasterizer boundary — replaces cuda_diff_fp.forward / backward
  * (diff_fp.cpp:21-67,77-129 -> diff_fp_for.cu:226-274, diff_fp_back.cu:297-350) together with the

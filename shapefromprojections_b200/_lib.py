@@ -26,6 +26,7 @@ _vp, _i, _sz, _u, _d, _f = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctyp
 SIGNATURES = {
     "ctdr_abi_version": (_i, []),
     "ctdr_last_error": (ctypes.c_char_p, []),
+    "ctdr_selftest_quotient": (_i, [ctypes.c_ulonglong, _u, _vp, _vp]),
     "ctdr_raster_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ctdr_raster_fragments_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ctdr_raster_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp, _u, _vp]),

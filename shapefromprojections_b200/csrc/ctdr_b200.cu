@@ -79,12 +79,12 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
     const long long blocks = (long long)P.B * P.regions_x * P.regions_y;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*regions too large for one launch");
     const size_t smem = raster_smem_bytes(P.n_mus);
-    if (flags & CTDR_FLAG_NO_PREFILTER) {
-        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-        k_raster<MODE, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-    } else {
+    if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate
         CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+    } else {
+        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+        k_raster<MODE, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     }
     CTDR_CUDA(cudaGetLastError(), "k_raster launch");
     return 0;
@@ -109,7 +109,7 @@ k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
     int ix0, iy0, ix1, iy1;
     if (!face_int_bbox(va.x, va.y, vb.x, vb.y, vc.x, vc.y, P.H, P.W, ix0, iy0, ix1, iy1)) return;
     const EdgeSetup es = edge_setup(va.x, va.y, vb.x, vb.y, vc.x, vc.y);
-    float M0 = 0.0f, Ms = 0.0f, Mt = 0.0f, A1 = 0.0f, A2 = 0.0f;
+    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
     const long long base = (long long)b * P.H * P.W;
     for (int y = iy0; y <= iy1; ++y)
         for (int x = ix0; x <= ix1; ++x) {
@@ -120,15 +120,15 @@ k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
             if (((double)v < -1e-5) || (v > P.msv)) continue;              // diff_fp_for.cu:69-73
             float s, t, k1, k2, w0, w1, w2;
             if (!cover_exact<PREFILTER>(es, (float)x, (float)y, s, t, k1, k2, w0, w1, w2)) continue;
-            M0 += g; Ms += g * s; Mt += g * t; A1 += g * k1; A2 += g * k2;
+            M0 += g; A1 += g * k1; A2 += g * k2;
         }
-    if (M0 == 0.0f && Ms == 0.0f && Mt == 0.0f && A1 == 0.0f && A2 == 0.0f) return;
+    if (M0 == 0.0f && A1 == 0.0f && A2 == 0.0f) return;
     float sgn = (__ldg(P.ff + gid) < 0.0f) ? -1.0f : 1.0f;
     if (lab.x == lab.y) sgn = -sgn;
     const float r0 = __ldg(P.len3 + gid * 3), r1 = __ldg(P.len3 + gid * 3 + 1), r2 = __ldg(P.len3 + gid * 3 + 2);
     const float cgeo = sgn * (__ldg(P.mus + lab.x) - __ldg(P.mus + lab.y));
     float gp[6], gl[3], bsum;
-    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, A1, A2, gp, gl, bsum);
+    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, A1, A2, gp, gl, bsum);
 #pragma unroll
     for (int k = 0; k < 6; ++k) P.grad_p6[gid * 6 + k] += gp[k];
 #pragma unroll
@@ -159,6 +159,37 @@ k_mus_reduce(const float* __restrict__ fs, const int* __restrict__ labels2, int 
         __syncthreads();
     }
     if (threadIdx.x == 0) grad_mus[l] += sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test: the hoisted-reciprocal quotient used by the raster kernels vs the compiler's IEEE
+// fp64 division, over pseudo-random (k1, k3) float pairs; counts bitwise mismatches of fl32(k1/d).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_selftest_quotient(unsigned long long per_thread, unsigned seed, unsigned long long* mismatches) {
+    unsigned long long x = ((unsigned long long)seed << 32) ^ (0x9E3779B97F4A7C15ULL * (blockIdx.x * blockDim.x + threadIdx.x + 1));
+    unsigned long long bad = 0;
+    for (unsigned long long it = 0; it < per_thread; ++it) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;                       // xorshift64
+        // exponents spread over 2^-40 .. 2^40, full random mantissas, both signs; every 64th sample
+        // is made tiny / zero / equal to exercise the corners
+        unsigned ua = (unsigned)x, ub = (unsigned)(x >> 32);
+        const unsigned ea = 87u + (ua >> 24) % 81u, eb = 87u + (ub >> 24) % 81u;
+        float k1 = __uint_as_float((ua & 0x807fffffu) | (ea << 23));
+        float k3 = __uint_as_float((ub & 0x807fffffu) | (eb << 23));
+        const unsigned sel = (unsigned)(x >> 17) & 63u;
+        if (sel == 0) k1 = (ua & 1u) ? 0.0f : -0.0f;
+        if (sel == 1) k3 = 0.0f;
+        if (sel == 2) k1 = k3;
+        if (sel == 3) k1 = __uint_as_float(ua & 0x800fffffu);           // denormal numerator
+        if (sel == 4) k3 = __uint_as_float((ub & 0x807fffffu) | (60u << 23));  // |k3| ~ 1e-20 (near eps)
+        const double d = (double)k3 + 1e-15;
+        const float ref = (float)((double)k1 / d);
+        const double y = 1.0 / d, a = (double)k1;
+        const double q0 = __dmul_rn(a, y);
+        const float got = (float)(k1 == 0.0f ? q0 : __fma_rn(__fma_rn(-q0, d, a), y, q0));
+        if (__float_as_uint(ref) != __float_as_uint(got) && !(ref != ref && got != got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 struct RasterWs {
@@ -300,6 +331,15 @@ int launch_vertex_backward(const VertexParams& P, const float* gp6, const float*
 extern "C" {
 
 int ctdr_abi_version(void) { return CTDR_ABI_VERSION; }
+
+int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned long long* mismatches, ctdr_stream_t stream) {
+    if (!mismatches) return fail(CTDR_E_NULL, "ctdr_selftest_quotient: null pointer");
+    const int blocks = 148 * 8, threads = 256;
+    const unsigned long long per = (samples + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+    k_selftest_quotient<<<blocks, threads, 0, stream>>>(per, seed, mismatches);
+    CTDR_CUDA(cudaGetLastError(), "k_selftest_quotient launch");
+    return 0;
+}
 const char* ctdr_last_error(void) { return g_err; }
 
 size_t ctdr_raster_workspace_bytes(int B, int F, int H, int W) {

@@ -88,15 +88,16 @@ k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
 // ------------------------------------------------------------------------------------------
 // shared memory
 // ------------------------------------------------------------------------------------------
+constexpr int SLOT_VEC = 5;       // float4 per staged face slot (stride 80 B: conflict-free LDS.128)
+
 struct __align__(16) WarpSmem {
-    // staged chunk: one slot per lane/face, structure of arrays (bank = slot index)
-    float ax[32], ay[32], m[32], p[32], n[32], q[32], k3[32];
-    float r0[32], r1[32], r2[32];
-    float cA[32], cB[32];        // forward: +sign*mu_in, -(sign*mu_out')   (diff_fp_for.cu:187,190)
-    int   box[32];               // lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13
-    int   excl[32];              // exclusive candidate offset of the slot
-    int   offs[32];              // inclusive candidate offsets (binary-searched)
-    float mom[5][32];            // backward: sum g, g*s, g*t, g*k1, g*k2 per slot
+    // Staged chunk, array of structures, nonempty faces compacted to the low slots:
+    //   v0 = (ax, ay, m, p)   v1 = (n, q, k3, box)   v2 = (d, 1/d) as two doubles
+    //   v3 = (r0, r1, r2, cA) v4 = (cB, excl, 1/k3, lane)
+    // box = lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13; excl = exclusive candidate offset of the slot;
+    // cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190).
+    float4 slot[32 * SLOT_VEC];
+    float mom[3][32];            // backward: sum g, sum g*k1, sum g*k2 per slot
     // tile accumulators
     float acc[TILE_PIX];         // forward: running sinogram; backward: g (0 where no gradient)
     int   cntv[TILE_PIX];        // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel
@@ -117,31 +118,32 @@ __device__ __forceinline__ bool box_overlap(const short4 bx, int x0, int y0, int
 }
 
 // segmented (by contiguous key) reduction toward the lowest lane of each run
-__device__ __forceinline__ void seg_reduce5(int key, int lane, float (&v)[5]) {
+__device__ __forceinline__ void seg_reduce3(int key, int lane, float (&v)[3]) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int kk = __shfl_down_sync(FULL, key, d);
-        float u[5];
+        float u[3];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) u[k] = __shfl_down_sync(FULL, v[k], d);
+        for (int k = 0; k < 3; ++k) u[k] = __shfl_down_sync(FULL, v[k], d);
         if (lane + d < 32 && kk == key) {
 #pragma unroll
-            for (int k = 0; k < 5; ++k) v[k] += u[k];
+            for (int k = 0; k < 3; ++k) v[k] += u[k];
         }
     }
 }
 
-
-// Gradients of one face from five moments of the upstream gradient g over the face's fragments:
-// M0 = sum g, Ms = sum g*s, Mt = sum g*t, A1 = sum g*k1, A2 = sum g*k2 (s = x0-ax, t = y0-ay, k1/k2
-// exactly as the forward computes them).  Every per-fragment term of diff_fp_back.cu:126-136
-// (grad_len), :143-147 (interpolated length * g, for grad_mus) and :206-292 (grad_points2d) is a
-// per-face constant times one of {1, s, t, k1, k2}, and s,t only ever appear multiplied by k3 — so
-// a zero-area face (k1 = k2 = k3 = 0) yields exact zeros like the reference, before the 1/(k3^2+eps)
-// factor.  cgeo = sign*(mu_in - mu_out): the two label iterations of back.cu:111 merged.
+// Gradients of one face from three moments of the upstream gradient g over the face's fragments:
+// M0 = sum g, A1 = sum g*k1, A2 = sum g*k2 (k1, k2 exactly as the forward computes them).
+// The per-fragment terms of diff_fp_back.cu:231-243 are  dw1/dn = -t*k3 + p*k1,  dw1/dq = s*k3 - m*k1,
+// dw2/dm = t*k3 - q*k2,  dw2/dp = -s*k3 + n*k2; with the identities  s*k3 = m*k1 + n*k2  and
+// t*k3 = p*k1 + q*k2  (k1 = s*q - n*t, k2 = m*t - s*p, k3 = m*q - n*p) they reduce to -q*k2, n*k2,
+// p*k1, -m*k1: every term is a per-face constant times one of {1, k1, k2}.  A zero-area face
+// (k1 = k2 = k3 = 0) therefore yields exact zeros like the reference, before the 1/(k3^2+eps) factor,
+// and the cancellation the reference suffers in fp32 (-t*k3 + p*k1) is avoided.
+// grad_len (:126-136) and the interpolated length (:143-147) use sum g*w_k = A_k/d.
+// cgeo = sign*(mu_in - mu_out): the two label iterations of back.cu:111 merged.
 __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, float r0, float r1, float r2,
-                                                        float cgeo, float M0, float Ms, float Mt,
-                                                        float A1, float A2,
+                                                        float cgeo, float M0, float A1, float A2,
                                                         float gp[6], float gl[3], float& bsum) {
     const float k3 = es.k3;
     const double dd = (double)k3 + 1e-15;
@@ -149,12 +151,12 @@ __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, flo
     const float W0 = M0 - W1 - W2;                            // sum g*w_k
     gl[0] = cgeo * W0; gl[1] = cgeo * W1; gl[2] = cgeo * W2;
     bsum = r0 * W0 + r1 * W1 + r2 * W2;
-    const float d1m = -es.q * A1,               d2m = k3 * Mt - es.q * A2;      // back.cu:231-243
-    const float d1n = -k3 * Mt + es.p * A1,     d2n = es.p * A2;
-    const float d1p = es.n * A1,                d2p = -k3 * Ms + es.n * A2;
-    const float d1q = k3 * Ms - es.m * A1,      d2q = -es.m * A2;
-    const float d1s = es.q * k3 * M0,           d2s = -es.p * k3 * M0;
-    const float d1t = -es.n * k3 * M0,          d2t = es.m * k3 * M0;
+    const float d1m = -es.q * A1,        d2m = es.p * A1;
+    const float d1n = -es.q * A2,        d2n = es.p * A2;
+    const float d1p = es.n * A1,         d2p = -es.m * A1;
+    const float d1q = es.n * A2,         d2q = -es.m * A2;
+    const float d1s = es.q * k3 * M0,    d2s = -es.p * k3 * M0;
+    const float d1t = -es.n * k3 * M0,   d2t = es.m * k3 * M0;
     const float c10 = r1 - r0, c20 = r2 - r0;                 // back.cu:271-280
     const float G0 = (float)((double)cgeo / ((double)(k3 * k3) + 1e-15));       // back.cu:282-283
     gp[0] = -G0 * (c10 * (d1m + d1n + d1s) + c20 * (d2m + d2n + d2s));          // back.cu:246-258
@@ -170,7 +172,7 @@ struct ThreadStats {
 // ------------------------------------------------------------------------------------------
 // one (tile, chunk): stage the chunk's faces, spread candidates over lanes, evaluate coverage
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool PREFILTER>
+template <int MODE, bool EXACT_DIV>
 __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S, float* gmus,
                                               int b, int chunk, int tx0, int ty0, int tx1, int ty1,
                                               int lane, ThreadStats& st) {
@@ -182,24 +184,22 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
     int ncand = 0;
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
-    int cx0 = 0, cy0 = 0, bw = 0;
+    int cx0 = 0, cy0 = 0, bw = 1;
     if (f < P.F) {
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
-        if (lab.x >= lab.y) {
-            const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
-            const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-            ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
-            int ix0, iy0, ix1, iy1;
-            if (face_int_bbox(ax, ay, bx, by, cx, cy, P.H, P.W, ix0, iy0, ix1, iy1)) {
-                cx0 = max(ix0, tx0); cy0 = max(iy0, ty0);
-                const int cx1 = min(ix1, tx1), cy1 = min(iy1, ty1);
-                bw = cx1 - cx0 + 1;
-                const int bh = cy1 - cy0 + 1;
-                if (bw > 0 && bh > 0) ncand = bw * bh;
-            }
+        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
+        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+        int ix0, iy0, ix1, iy1;
+        if (lab.x >= lab.y && face_int_bbox(ax, ay, bx, by, cx, cy, P.H, P.W, ix0, iy0, ix1, iy1)) {
+            cx0 = max(ix0, tx0); cy0 = max(iy0, ty0);
+            const int cx1 = min(ix1, tx1), cy1 = min(iy1, ty1);
+            const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
+            if (w > 0 && h > 0) { ncand = w * h; bw = w; }
         }
     }
-    if (__ballot_sync(FULL, ncand > 0) == 0u) return;
+    const unsigned nz = __ballot_sync(FULL, ncand > 0);
+    if (nz == 0u) return;
 
     int incl = ncand;
 #pragma unroll
@@ -208,16 +208,21 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         if (lane >= d) incl += v;
     }
     const int T = __shfl_sync(FULL, incl, 31);
+    const int nslots = __popc(nz);
+    const int rank = __popc(nz & lanemask_lt());       // compacted slot of this lane's face
 
-    // per-face gradient constants kept in registers by the owning lane (backward only)
+    // per-face constants kept in registers by the owning lane (backward epilogue)
     float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
-    EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
-    S.offs[lane] = incl;
+    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
     if (ncand > 0) {
-        S.ax[lane] = es.ax; S.ay[lane] = es.ay; S.m[lane] = es.m; S.p[lane] = es.p;
-        S.n[lane] = es.n; S.q[lane] = es.q; S.k3[lane] = es.k3;
-        S.box[lane] = (cx0 - tx0) | ((cy0 - ty0) << 4) | (bw << 8) | (((8192 + bw - 1) / bw) << 13);
-        S.excl[lane] = incl - ncand;
+        float4* sl = S.slot + rank * SLOT_VEC;
+        const int box = (cx0 - tx0) | ((cy0 - ty0) << 4) | (bw << 8) |
+                        (__float2int_ru(8192.0f * __frcp_rn((float)bw)) << 13);
+        sl[0] = make_float4(es.ax, es.ay, es.m, es.p);
+        sl[1] = make_float4(es.n, es.q, es.k3, __int_as_float(box));
+        const double d = (double)es.k3 + 1e-15;                        // diff_fp_for.cu:144 denominator
+        reinterpret_cast<double2*>(sl)[2] = make_double2(d, 1.0 / d);
+        float cA = 0.0f, cB = 0.0f;
         if (!IS_FRAG) {
             const float* pl = P.len3 + bf * 3;
             r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
@@ -228,61 +233,91 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
             const float mu_in = __ldg(P.mus + lab.x);
             float mu_out = __ldg(P.mus + lab.y);
             if (lab.y == 0) mu_out = -mu_out;                         // :174-175
-            S.r0[lane] = r0; S.r1[lane] = r1; S.r2[lane] = r2;
-            S.cA[lane] = __fmul_rn(sgn, mu_in);                       // :187
-            S.cB[lane] = -__fmul_rn(sgn, mu_out);                     // :190
+            cA = __fmul_rn(sgn, mu_in);                               // :187
+            cB = -__fmul_rn(sgn, mu_out);                             // :190
+            sl[3] = make_float4(r0, r1, r2, cA);
         }
-        if (IS_BWD) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) S.mom[k][lane] = 0.0f;
-        }
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), __frcp_rn(es.k3), __int_as_float(lane));
+        if (IS_BWD) { S.mom[0][rank] = 0.0f; S.mom[1][rank] = 0.0f; S.mom[2][rank] = 0.0f; }
     }
     __syncwarp();
+    // lane r < nslots tracks the first candidate of compacted slot r ("segment heads")
+    const int myexcl = (lane < nslots) ? __float_as_int(S.slot[lane * SLOT_VEC + 4].y) : 0x3fffffff;
+    int nbefore = 0;                                    // slots starting before `base`
 
     for (int base = 0; base < T; base += 32) {
-        const int j = base + lane;
-        const bool act = j < T;
-        const int jj = act ? j : T - 1;
-        int i = 0;                                   // smallest slot with offs[i] > jj
-        if (S.offs[i + 15] <= jj) i += 16;
-        if (S.offs[i + 7] <= jj) i += 8;
-        if (S.offs[i + 3] <= jj) i += 4;
-        if (S.offs[i + 1] <= jj) i += 2;
-        if (S.offs[i] <= jj) i += 1;
-        const int e = jj - S.excl[i];
-        const int box = S.box[i];
+        // which slot owns candidate base+lane: count the segment heads at or before this lane
+        const unsigned hp = (unsigned)(myexcl - base);
+        const unsigned heads = __reduce_or_sync(FULL, hp < 32u ? (1u << hp) : 0u);
+        const int i = nbefore + __popc(heads & (lanemask_lt() | (1u << lane))) - 1;
+        nbefore += __popc(heads);
+        const bool act = base + lane < T;
+        const float4* sl = S.slot + i * SLOT_VEC;
+        const float4 v0 = sl[0], v1 = sl[1], v4 = sl[4];
+        const int e = base + lane - __float_as_int(v4.y);
+        const int box = __float_as_int(v1.w);
         const int w = (box >> 8) & 31;
         const int ly = (e * (box >> 13)) >> 13;
         const int lx = e - ly * w;
         const int px = (box & 15) + lx, py = ((box >> 4) & 15) + ly;
-        const int pl = py * TILE + px;
-        EdgeSetup c;
-        c.ax = S.ax[i]; c.ay = S.ay[i]; c.m = S.m[i]; c.p = S.p[i]; c.n = S.n[i]; c.q = S.q[i]; c.k3 = S.k3[i];
-        float s, t, k1, k2, w0, w1, w2;
-        bool in = cover_exact<PREFILTER>(c, (float)(tx0 + px), (float)(ty0 + py), s, t, k1, k2, w0, w1, w2);
-        in = in && act;
+        const int pl = (py * TILE + px) & (TILE_PIX - 1);
+        // coverage: diff_fp_for.cu:132-151, bit-identical (see cover_exact for the prefilter argument)
+        const float s = __fsub_rn((float)(tx0 + px), v0.x), t = __fsub_rn((float)(ty0 + py), v0.y);
+        const float k1 = __fmaf_rn(s, v1.y, -__fmul_rn(v1.x, t));
+        const float k2 = __fmaf_rn(v0.z, t, -__fmul_rn(s, v0.w));
+        const float k3 = v1.z;
+        bool in = act;
+        if (!EXACT_DIV) {
+            const float ak3 = fabsf(k3);
+            if ((ak3 > 1e-6f) & (ak3 < 1e10f)) {
+                const bool dneg = k3 < 0.0f;
+                if (fabsf(k1) > 1e-30f && ((k1 < 0.0f) != dneg)) in = false;
+                if (fabsf(k2) > 1e-30f && ((k2 < 0.0f) != dneg)) in = false;
+                const float a1 = k1 * v4.z, a2 = k2 * v4.z;
+                if (1.0f - a1 - a2 < -1e-4f * (1.0f + fabsf(a1) + fabsf(a2))) in = false;
+            }
+        }
+        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
+        if (in) {
+            const double2 dy = reinterpret_cast<const double2*>(sl)[2];
+            if (EXACT_DIV) {
+                w1 = (float)((double)k1 / dy.x);
+                w2 = (float)((double)k2 / dy.x);
+            } else {
+                // IEEE quotient from the face's reciprocal: q0 = a*y, r = a - q0*d (exact), q = q0 + r*y
+                // (the correction step of the compiler's own fp64 division, with 1/d hoisted per face)
+                // A zero numerator keeps q0 = (+-0)*y: the correction step would turn -0 into +0.
+                const double a1 = (double)k1, a2 = (double)k2;
+                const double q1 = __dmul_rn(a1, dy.y), q2 = __dmul_rn(a2, dy.y);
+                w1 = (float)(k1 == 0.0f ? q1 : __fma_rn(__fma_rn(-q1, dy.x, a1), dy.y, q1));
+                w2 = (float)(k2 == 0.0f ? q2 : __fma_rn(__fma_rn(-q2, dy.x, a2), dy.y, q2));
+            }
+            w0 = __fsub_rn(__fsub_rn(1.0f, w1), w2);
+            in = !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+        }
         if (act) st.cand++;
 
         if (IS_FWD) {
-            float bary = 0.0f, cA = 0.0f, cB = 0.0f;
+            float bary = 0.0f, cA = 0.0f;
             if (in) {
-                bary = __fmaf_rn(w2, S.r2[i], __fmaf_rn(w0, S.r0[i], __fmul_rn(w1, S.r1[i])));  // :182
-                cA = S.cA[i]; cB = S.cB[i];
+                const float4 v3 = sl[3];
+                bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));  // :182
+                cA = v3.w;
                 if (!(bary > 0.0f)) st.nonpos++;                      // :183 assert -> counter
                 st.frag++;
             }
             const unsigned inm = __ballot_sync(FULL, in);
             if (inm) {
-                int rank = -1, np = 0;
+                int rk = -1, np = 0;
                 if (in) {
                     const unsigned peers = __match_any_sync(inm, pl);  // same pixel, different faces
-                    rank = __popc(peers & lanemask_lt());
+                    rk = __popc(peers & lanemask_lt());
                     np = __popc(peers);
                 }
                 const int rounds = __reduce_max_sync(FULL, np);
                 for (int r = 0; r < rounds; ++r) {                   // ascending lane == ascending face id
-                    if (rank == r) {
-                        S.acc[pl] = __fmaf_rn(bary, cB, __fmaf_rn(bary, cA, S.acc[pl]));
+                    if (rk == r) {
+                        S.acc[pl] = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, cA, S.acc[pl]));
                         S.cntv[pl] += 1;                              // :192
                     }
                     __syncwarp();
@@ -292,20 +327,20 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
             if (in && S.cntv[pl] < 0) in = false;                     // invalid pixel (:69-73)
             const unsigned inm = __ballot_sync(FULL, in);
             if (inm) {
-                int rank = -1, np = 0;
+                int rk = -1, np = 0;
                 if (in) {
                     const unsigned peers = __match_any_sync(inm, pl);
-                    rank = __popc(peers & lanemask_lt());
+                    rk = __popc(peers & lanemask_lt());
                     np = __popc(peers);
                 }
                 const int rounds = __reduce_max_sync(FULL, np);
                 for (int r = 0; r < rounds; ++r) {
-                    if (rank == r) {
+                    if (rk == r) {
                         const int k = S.cntv[pl];
                         S.cntv[pl] = k + 1;
                         const long long pix = ((long long)b * P.H + (ty0 + py)) * P.W + (tx0 + px);
                         const long long slot = (long long)__ldg(P.firstidx + pix) + k;  // :208-209
-                        P.imidx[slot] = chunk * CHUNK + i + 1;        // :212
+                        P.imidx[slot] = chunk * CHUNK + __float_as_int(v4.w) + 1;       // :212
                         P.imwei[3 * slot + 0] = w0;
                         P.imwei[3 * slot + 1] = w1;
                         P.imwei[3 * slot + 2] = w2;                   // :214-216
@@ -316,13 +351,12 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         } else {  // backward: per-face moments of the upstream gradient
             float g = 0.0f;
             if (in) { g = S.acc[pl]; if (g != 0.0f) st.frag++; }
-            float v[5] = {g, g * s, g * t, g * k1, g * k2};
+            float v[3] = {g, g * k1, g * k2};
             if (__ballot_sync(FULL, g != 0.0f)) {
-                seg_reduce5(i, lane, v);
+                seg_reduce3(i, lane, v);
                 const int iprev = __shfl_up_sync(FULL, i, 1);
                 if (lane == 0 || iprev != i) {        // run head: distinct slots, no conflicts
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) S.mom[k][i] += v[k];
+                    S.mom[0][i] += v[0]; S.mom[1][i] += v[1]; S.mom[2][i] += v[2];
                 }
                 __syncwarp();
             }
@@ -330,14 +364,13 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
     }
 
     if (IS_BWD && ncand > 0) {
-        // per-face gradients from the five moments of this tile's fragments (face_grads_from_moments)
-        const float M0 = S.mom[0][lane], Ms = S.mom[1][lane], Mt = S.mom[2][lane];
-        const float A1 = S.mom[3][lane], A2 = S.mom[4][lane];
-        if (M0 != 0.0f || Ms != 0.0f || Mt != 0.0f || A1 != 0.0f || A2 != 0.0f) {
+        // per-face gradients from the moments of this tile's fragments (face_grads_from_moments)
+        const float M0 = S.mom[0][rank], A1 = S.mom[1][rank], A2 = S.mom[2][rank];
+        if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
             const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
             const float cgeo = sgn * (mu_in - mu_out);                // raw mu, no label-0 flip (back.cu:115)
             float gp[6], gl[3], bsum;
-            face_grads_from_moments(es, r0, r1, r2, cgeo, M0, Ms, Mt, A1, A2, gp, gl, bsum);
+            face_grads_from_moments(es, r0, r1, r2, cgeo, M0, A1, A2, gp, gl, bsum);
             float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
             atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
             // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
@@ -392,7 +425,7 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // ------------------------------------------------------------------------------------------
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool PREFILTER>
+template <int MODE, bool EXACT_DIV>
 __global__ void __launch_bounds__(THREADS)
 k_raster(const RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -559,7 +592,7 @@ k_raster(const RasterParams P) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
                     const int chunk = __shfl_sync(FULL, cid, src);
-                    process_chunk<MODE, PREFILTER>(P, S, gmus, b, chunk, tx0, ty0, tx1, ty1, lane, st);
+                    process_chunk<MODE, EXACT_DIV>(P, S, gmus, b, chunk, tx0, ty0, tx1, ty1, lane, st);
                 }
             }
 

@@ -177,3 +177,14 @@ def test_errors_are_loud(cuda_lib):
         R.raster_forward(dev(c["p6"]).double(), dev(c["len3"]), dev(c["ff"]), dev(c["labels"]), dev(c["mus"]), 16, 16, 1.0)
     with pytest.raises(RuntimeError):
         R.raster_forward(dev(c["p6"]), dev(c["len3"]), dev(c["ff"]), dev(c["labels"]), dev(c["mus"]), 40000, 16, 1.0)
+
+
+def test_hoisted_reciprocal_quotient_is_ieee(cuda_lib):
+    """The only arithmetic shortcut in the kernels: k1/d from the face's 1/d + one fma correction must
+    equal the reference's IEEE fp64 division bit for bit (2^32 random float pairs, incl. corner cases)."""
+    from shapefromprojections_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 2):
+        _lib.check(cuda_lib.ctdr_selftest_quotient(1 << 31, seed, bad.data_ptr(), _lib.stream_ptr(bad.device)), "selftest")
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
