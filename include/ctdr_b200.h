@@ -55,6 +55,8 @@ extern "C" {
 #define CTDR_STAT_FRAGMENTS       1 /* covered (pixel, face) pairs == the reference's `vf` (rasterizer.py:64) */
 #define CTDR_STAT_CANDIDATES      2 /* bbox (pixel, face) pairs evaluated */
 #define CTDR_STAT_LIST_SEGMENTS   3 /* extra chunk-list segments taken (0 unless > capacity chunks hit a region) */
+#define CTDR_STAT_CHUNK_VISITS    4 /* (tile, chunk) pairs whose 32 faces were staged */
+#define CTDR_STAT_CHUNK_HITS      5 /* ... of which at least one face had a candidate pixel in the tile */
 #define CTDR_STAT_COUNT           8
 
 /* geometry kinds for the vertex stage */

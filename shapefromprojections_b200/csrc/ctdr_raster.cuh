@@ -166,7 +166,21 @@ __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, flo
 }
 
 struct ThreadStats {
-    unsigned int cand, frag, nonpos;
+    unsigned int cand, frag, nonpos, visits, hits;   // visits/hits: (tile, chunk) pairs staged / with candidates
+    // Attenuation gradient: each lane keeps a running sum per (label_in, label_out) pair and only
+    // touches the CTA's shared accumulators when its face's labels change (meshes carry long runs
+    // of equal labels), instead of two contended shared-memory atomics per (tile, face).
+    int lab_in, lab_out;
+    float sum_in, sum_out;
+    __device__ __forceinline__ void mus_flush(float* gmus) {
+        if (sum_in != 0.0f) atomicAdd(gmus + lab_in, sum_in);
+        if (sum_out != 0.0f) atomicAdd(gmus + lab_out, sum_out);
+        sum_in = 0.0f; sum_out = 0.0f;
+    }
+    __device__ __forceinline__ void mus_add(float* gmus, int li, float vi, int lo, float vo) {
+        if (li != lab_in || lo != lab_out) { mus_flush(gmus); lab_in = li; lab_out = lo; }
+        sum_in += vi; sum_out += vo;
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -199,6 +213,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         }
     }
     const unsigned nz = __ballot_sync(FULL, ncand > 0);
+    if (lane == 0) { st.visits++; st.hits += (nz != 0u); }
     if (nz == 0u) return;
 
     int incl = ncand;
@@ -237,7 +252,9 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
             cB = -__fmul_rn(sgn, mu_out);                             // :190
             sl[3] = make_float4(r0, r1, r2, cA);
         }
-        sl[4] = make_float4(cB, __int_as_float(incl - ncand), __frcp_rn(es.k3), __int_as_float(lane));
+        const float ak3 = fabsf(es.k3);
+        const float rd = ((ak3 > 1e-6f) & (ak3 < 1e10f)) ? __frcp_rn(es.k3) : 0.0f;
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), rd, __int_as_float(lane));
         if (IS_BWD) { S.mom[0][rank] = 0.0f; S.mom[1][rank] = 0.0f; S.mom[2][rank] = 0.0f; }
     }
     __syncwarp();
@@ -268,14 +285,13 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         const float k3 = v1.z;
         bool in = act;
         if (!EXACT_DIV) {
-            const float ak3 = fabsf(k3);
-            if ((ak3 > 1e-6f) & (ak3 < 1e10f)) {
-                const bool dneg = k3 < 0.0f;
-                if (fabsf(k1) > 1e-30f && ((k1 < 0.0f) != dneg)) in = false;
-                if (fabsf(k2) > 1e-30f && ((k2 < 0.0f) != dneg)) in = false;
-                const float a1 = k1 * v4.z, a2 = k2 * v4.z;
-                if (1.0f - a1 - a2 < -1e-4f * (1.0f + fabsf(a1) + fabsf(a2))) in = false;
-            }
+            // Prefilter (see cover_exact in ctdr_common.cuh for the argument): v4.z = 1/k3, or 0 when
+            // |k3| is outside (1e-6, 1e10) — then a1 = a2 = 0 and every test below passes.
+            // a < -1e-30 => the fp64 quotient is strictly negative and far from underflow => w < 0;
+            // the fp32 estimate of w0 = 1 - w1 - w2 is within ~5e-7*(1+|w1|+|w2|) of the reference value.
+            const float a1 = k1 * v4.z, a2 = k2 * v4.z;
+            if (fminf(a1, a2) < -1e-30f) in = false;
+            if ((1.0f - a1) - a2 < -1e-4f * ((1.0f + fabsf(a1)) + fabsf(a2))) in = false;
         }
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
         if (in) {
@@ -318,7 +334,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
                 for (int r = 0; r < rounds; ++r) {                   // ascending lane == ascending face id
                     if (rk == r) {
                         S.acc[pl] = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, cA, S.acc[pl]));
-                        S.cntv[pl] += 1;                              // :192
+                        if (P.cnt) S.cntv[pl] += 1;                   // :192
                     }
                     __syncwarp();
                 }
@@ -374,8 +390,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
             float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
             atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
             // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
-            atomicAdd(gmus + lab.x, (lab.x == 0 ? -sgn : sgn) * bsum);
-            atomicAdd(gmus + lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
+            st.mus_add(gmus, lab.x, (lab.x == 0 ? -sgn : sgn) * bsum, lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
             float* dp = P.grad_p6 + bf * 6;                           // back.cu:285-292
 #pragma unroll
             for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
@@ -426,7 +441,7 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool EXACT_DIV>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 k_raster(const RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaSmem& C = *reinterpret_cast<CtaSmem*>(smem_raw);
@@ -440,7 +455,7 @@ k_raster(const RasterParams P) {
     const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
     const short4* boxes = P.chunk_box + (long long)b * P.NC;
     WarpSmem& S = C.warp[warp];
-    ThreadStats st = {0u, 0u, 0u};
+    ThreadStats st = {0u, 0u, 0u, 0u, 0u, 0, 0, 0.0f, 0.0f};
 
     constexpr bool K_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
     double loss_acc = 0.0;
@@ -615,6 +630,7 @@ k_raster(const RasterParams P) {
     } while (c < P.NC);
 
     if (K_BWD) {
+        st.mus_flush(gmus);
         __syncthreads();
         for (int k = tid; k < P.n_mus; k += THREADS) {
             const float v = gmus[k];
@@ -635,10 +651,14 @@ k_raster(const RasterParams P) {
         const unsigned cand = __reduce_add_sync(FULL, st.cand);
         const unsigned frag = __reduce_add_sync(FULL, st.frag);
         const unsigned nonpos = __reduce_add_sync(FULL, st.nonpos);
+        const unsigned visits = __reduce_add_sync(FULL, st.visits);
+        const unsigned hits = __reduce_add_sync(FULL, st.hits);
         if (lane == 0) {
             if (nonpos) atomicAdd(P.stats + 0, (unsigned long long)nonpos);
             if (frag) atomicAdd(P.stats + 1, (unsigned long long)frag);
             if (cand) atomicAdd(P.stats + 2, (unsigned long long)cand);
+            if (visits) atomicAdd(P.stats + 4, (unsigned long long)visits);
+            if (hits) atomicAdd(P.stats + 5, (unsigned long long)hits);
             if (warp == 0 && seg > 1) atomicAdd(P.stats + 3, (unsigned long long)(seg - 1));
         }
     }
