@@ -1,0 +1,142 @@
+"""The optimiser loop (``ctdr/optimize.py:95-257``): Adam over ``displace`` and ``mus`` against the
+masked-L2 data term plus edge / Laplacian / flatten regularisers, same ``log.txt`` line format.
+
+``run(model, ds, niter, args, epoch_start=0, use_adam=True)`` keeps the reference signature.  Two
+data paths: the autograd path (``model(idx_angles, wedge)`` like the reference) and, with
+``fused=True`` (default when the model uses the fused projector), ``projection_step`` — one
+device sweep that forms the residual, the loss and the gradients without the reference's three
+host syncs per iteration (``rasterizer.py:64``, ``fp_vecs.py:18``, the boolean-mask index at
+``optimize.py:168``) and all-reduces them when angles are sharded over several GPUs.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from . import distributed
+from .function import rasterizer as R
+from .utils import util_mesh, util_vis
+
+
+def get_params(model, exclude_mus=False):
+    return model.parameters()
+
+
+def projection_step(model, idx_angles, p_batch, exchange=None):
+    """Data term of one iteration through the fused device path.
+
+    Sets ``.grad`` of ``model.displace`` / ``model.mus`` (adding to existing gradients) to the
+    gradient of ``mean_valid (p - phat)^2`` and returns ``(data_loss, phat, n_valid)`` as device
+    tensors.  With several ranks, each passes its own angle shard and the sums are all-reduced.
+    """
+    fp = model.fp
+    verts = model.get_displaced_vertices().detach().contiguous()
+    if model.mus_fixed_no == 1:
+        model.mus.data[0] = model.p_min
+    mus = model.mus.detach().contiguous()
+    dev = verts.device
+    if exchange is None:
+        exchange = distributed.GradientExchange(verts.shape[0], mus.numel(), dev)
+    exchange.zero_()
+    idx = torch.as_tensor(idx_angles).to(device=dev, dtype=torch.int64)
+    phat, _, _, _ = R.project_residual_step(fp.geom, verts, fp._faces32(model.faces), fp.labels_fx2, mus, idx,
+                                            p_batch.contiguous(), grad_verts=exchange.grad_verts,
+                                            grad_mus=exchange.grad_mus, out2=exchange.scalars)
+    exchange.all_reduce()
+    gverts, gmus, loss = exchange.mean_gradients()
+    for prm, g in ((model.displace, gverts), (model.mus, gmus)):
+        if isinstance(prm, torch.nn.Parameter) and prm.requires_grad:
+            prm.grad = g.clone() if prm.grad is None else prm.grad + g
+    return loss.to(torch.float32), phat, exchange.scalars[1]
+
+
+def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_every=60):
+    if fused is None:
+        fused = getattr(model.fp, "fused", False)
+    print("@ model.mus", model.mus)
+    params = list(get_params(model))
+    opt = (torch.optim.Adam(params, args.lr, betas=(0.9, 0.99)) if use_adam
+           else torch.optim.SGD(params, lr=args.lr, momentum=0.9, nesterov=True))
+    f = open(args.dresult + "log.txt", "w" if epoch_start == 0 else "a")
+    log = f"@ statistics of mesh: {model.vertices.shape[0]}, {model.faces.shape[0]}\n"
+    dev = model.vertices.device
+    if args.b == 0:
+        ds_loader = [[torch.arange(ds.nangles), ds.p.to(dev)]]
+    else:
+        ds_loader = torch.utils.data.DataLoader(ds, batch_size=args.b, shuffle=True, num_workers=0,
+                                                drop_last=True, pin_memory=True)
+    exchange = distributed.GradientExchange(model.vertices.shape[0], model.mus.numel(), dev) if fused else None
+    ledge = llap = lflat = 0.
+    loss_prev = None
+    phat = mask_valid = None
+    for epoch in range(epoch_start, niter):
+        if epoch + 100 == niter and niter > 400:
+            for group in opt.param_groups:
+                group["lr"] *= 0.5
+            args.lr *= 0.5
+            print("@ args.lr", args.lr)
+        torch.cuda.synchronize(dev)
+        start = time.time()
+        for idx_angles, p_batch in ds_loader:
+            if args.b > 0:
+                p_batch = p_batch.to(dev, non_blocking=True)
+            opt.zero_grad()
+            if fused:
+                data_loss, phat, _ = projection_step(model, idx_angles, p_batch, exchange)
+                vertices = model.get_displaced_vertices()
+                edge_loss = R_edge(model, vertices) if args.wedge > 0. else 0.
+                lap_loss = model.laplacian_loss(vertices).mean() if model.use_lap_loss else 0.
+                flat_loss = model.flat_loss(vertices) if model.use_flat_loss else 0.
+                reg = args.wedge * edge_loss + args.wlap * lap_loss + args.wflat * flat_loss
+                if torch.is_tensor(reg):
+                    reg.backward()                     # adds to the gradients set by projection_step
+                loss = data_loss + (reg.detach() if torch.is_tensor(reg) else reg)
+                mask_valid = None
+            else:
+                phat, mask_valid, edge_loss, lap_loss, flat_loss = model(idx_angles, args.wedge)
+                data_loss = (p_batch - phat)[mask_valid].pow(2).mean()
+                loss = data_loss + args.wedge * edge_loss + args.wlap * lap_loss + args.wflat * flat_loss
+                loss.backward()
+            opt.step()
+            model.mus.data.clamp_(min=0.0)
+        loss_now = float(loss)                        # the one host sync of the iteration
+        elapsed = time.time() - start
+        if loss_prev is not None and args.b == 0 and 0 < loss_prev - loss_now < 1e-11:
+            print("! converged")
+            break
+        loss_prev = loss_now
+        ledge = float(edge_loss) if args.wedge > 0. else ledge
+        llap = float(lap_loss) if args.wlap > 0. else llap
+        lflat = float(flat_loss) if args.wflat > 0. else lflat
+        log += (f"~ {epoch:03d} l2_loss: {float(data_loss):.8f} edge: {ledge:.6f} lap: {llap:.6f} flat: {lflat:.6f} "
+                f"mus: {str(model.mus.cpu().detach().numpy())} time: {elapsed:.4f}\n")
+        if epoch % log_every == 0 or epoch == niter - 1:
+            if mask_valid is None:
+                from .nn.fp_vecs import get_valid_mask
+                mask_valid = get_valid_mask(phat, model.fp.max_sino_val)
+            if torch.sum(~mask_valid) > 15000 and epoch > 100:
+                raise AssertionError("consider increasing regularization")
+            print(log)
+            if args.b == 0 and ds.p_original is not None:
+                res_np = ds.p_original - phat.detach().cpu().numpy()
+                f.write(f"~ res_np: {np.mean(res_np ** 2)}\n")
+                util_vis.save_sino_as_img(args.dresult + f"{epoch:04d}_sino_res.png", res_np, cmap="coolwarm")
+            if getattr(args, "verbose", 0) == 0:
+                continue
+            vv = (model.vertices + model.displace.detach()).cpu()
+            util_vis.save_sino_as_img(args.dresult + f"{epoch:04d}_sino.png", phat.detach().cpu().numpy())
+            util_mesh.save_mesh(args.dresult + f"{epoch:04d}.obj", vv.numpy(), model.faces.cpu().numpy(),
+                                model.labels_v_np, model.labels.cpu().numpy())
+            if epoch == niter - 1:
+                util_mesh.save_mesh(args.dresult + "mesh.obj", vv.numpy(), model.faces.cpu().numpy(),
+                                    model.labels_v_np, model.labels.cpu().numpy())
+    f.write(log + "\n")
+    f.close()
+    return phat
+
+
+def R_edge(model, vertices):
+    from .utils import util_fun
+    return util_fun.compute_edge_length(vertices, model.faces)

@@ -1,0 +1,104 @@
+"""GPU tests of the callers either side of the hot path: Model.forward and the optimiser iteration."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(geom, subdiv=3, wlap=10.0, wflat=0.01, nmu0=1):
+    from ctdr.model.vanilla import Model               # the reference's import path (drop-in package)
+    verts, faces, labels, mus = cases.sphere_mesh(subdiv, 0.4)
+    labels_v = np.ones(verts.shape[0], dtype=np.int32)
+    return Model((verts, faces, labels_v, labels), geom, 2, [0.0, 1.0], nmu0, wlap=wlap, wflat=wflat).cuda()
+
+
+def target_sinogram(geom, scale=(1.2, 0.9, 1.1)):
+    """Config-1 style target: projection of the same sphere scaled anisotropically."""
+    m = make_model(geom, wlap=0.0, wflat=0.0)
+    with torch.no_grad():
+        m.vertices *= torch.tensor(scale, device="cuda")
+        phat, _, _, _, _ = m(torch.arange(m.nangles), 0.0, backprop=False)
+    return phat.detach()
+
+
+def test_model_forward_surface(cuda_lib):
+    geom = cases.parallel_geometry(8, 96, 2.0 / 96)
+    model = make_model(geom)
+    phat, mask, edge, lap, flat = model(torch.arange(8), 2.0)
+    assert phat.shape == (8, 96, 96) and mask.dtype == torch.bool and mask.all()
+    assert edge > 0 and lap >= 0 and 0 <= flat < 0.1
+    (phat.sum() + edge + lap + flat).backward()
+    assert model.displace.grad.abs().max() > 0 and model.mus.grad is not None
+    ph2, _ = model.render()
+    assert torch.equal(ph2, phat.detach())
+    v, f, lv, lf = model.get_vf_np()
+    assert v.shape == (model.vertices.shape[0], 3) and lf.shape == (f.shape[0], 2)
+    assert abs(phat.max().item() - 0.8) < 0.02          # chord through the centre of an r = 0.4 sphere
+
+
+def test_fused_iteration_equals_autograd_iteration(cuda_lib):
+    """projection_step (one device sweep, no host sync) gives the loss and gradients of the
+    reference's formulation (optimize.py:162-190) evaluated through autograd."""
+    from ctdr import optimize
+    geom = cases.parallel_geometry(8, 96, 2.0 / 96)
+    p = target_sinogram(geom)
+    a, b = make_model(geom, wlap=0.0, wflat=0.0), make_model(geom, wlap=0.0, wflat=0.0)
+    idx = torch.arange(8)
+    phat, mask, _, _, _ = a(idx, 0.0)
+    loss = (p - phat)[mask].pow(2).mean()
+    loss.backward()
+    loss_f, phat_f, _ = optimize.projection_step(b, idx, p)
+    assert torch.equal(phat_f, phat.detach())
+    assert abs(loss_f.item() - loss.item()) <= 1e-5 * loss.item()
+    assert (b.displace.grad - a.displace.grad).norm() <= 2e-5 * a.displace.grad.norm()
+    assert (b.mus.grad - a.mus.grad).norm() <= 2e-5 * a.mus.grad.norm() + 1e-9
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_optimise_run_reduces_the_data_loss(cuda_lib, tmp_path, fused):
+    """Short config-1 style reconstruction (sphere -> anisotropically scaled sphere): the loss drops
+    by more than an order of magnitude and log.txt keeps the reference's line format."""
+    from ctdr import optimize
+    from ctdr.dataset.dataset import SinoDataset
+    geom = cases.parallel_geometry(12, 96, 2.0 / 96)
+    p = target_sinogram(geom)
+    ds = SinoDataset.from_arrays(geom, p.cpu().numpy(), nmaterials=2, eta=0.0)
+    model = make_model(geom, wlap=10.0, wflat=0.0)
+    model.set_mu0(ds.p.cuda())
+    args = types.SimpleNamespace(data="2starA", lr=0.01, b=0, wedge=1.0, wlap=10.0, wflat=0.0, verbose=0,
+                                 dresult=str(tmp_path) + "/")
+    optimize.run(model, ds, 60, args, fused=fused)
+    lines = [l for l in open(tmp_path / "log.txt").read().splitlines() if l.startswith("~ 0")]
+    assert len(lines) == 60 and " l2_loss: " in lines[0] and " mus: " in lines[0] and " time: " in lines[0]
+    first = float(lines[0].split("l2_loss:")[1].split()[0]); last = float(lines[-1].split("l2_loss:")[1].split()[0])
+    assert last < first / 10, (first, last)
+    assert model.mus.data[1].item() > 0.9
+
+
+def test_reference_rasterizer_module_runs_on_new_kernels(cuda_lib):
+    """The cuda_diff_fp-compatible module reproduces Rasterizer.forward/backward of the reference flow
+    (pass 1, cumsum/firstidx, pass 2, backward) — exercised with this repo's restatement of that flow."""
+    import sys
+    from shapefromprojections_b200 import cuda_diff_fp as compat
+    from oracle import ref_driver
+    c = cases.soup_case(5, B=2, F=900, H=64, W=64, reference_safe=True)
+    saved = ref_driver._mod
+    try:
+        ref_driver._mod = compat                      # drive OUR kernels through the reference's host steps
+        fwd = ref_driver.forward(c["p6"], c["len3"], c["ff"], c["labels"], c["mus"], c["H"], c["W"], c["msv"])
+        g = np.random.default_rng(1).normal(size=(2, 64, 64, 1)).astype(np.float32)
+        dp, dl, dm = ref_driver.backward(fwd, g)
+    finally:
+        ref_driver._mod = saved
+    from oracle import oracle
+    o = oracle.rasterizer_forward(c["p6"], c["len3"], c["ff"], c["labels"], c["mus"], c["H"], c["W"], c["msv"], True, fast=True)
+    assert np.array_equal(fwd["imidx"].cpu().numpy(), o["imidx"]) and np.array_equal(fwd["cnt"].cpu().numpy(), o["cnt"])
+    assert np.array_equal(fwd["im"].cpu().numpy().view(np.uint32), o["im"].view(np.uint32))
+    od = oracle.rasterizer_backward(g, o, c["p6"], c["len3"], c["ff"], c["labels"], c["mus"])
+    for a, b in zip((dp, dl, dm), od):
+        assert np.linalg.norm(a.cpu().numpy() - b) <= 2e-4 * np.linalg.norm(b)
