@@ -353,7 +353,7 @@ def kernel_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, pha
         st = st.tolist()
         out["fragments"] = st[_lib.STAT_FRAGMENTS]; out["candidates"] = st[_lib.STAT_CANDIDATES]
         out["nonpositive_len"] = st[_lib.STAT_NONPOSITIVE_LEN]; out["list_segments"] = st[_lib.STAT_LIST_SEGMENTS]
-        out["chunk_visits"] = st[4]; out["chunk_hits"] = st[5]
+        out["face_batches"] = st[4]; out["chunk_hits"] = st[5]
         out["full_forward_ms"] = timed(lambda: R.project_forward(gd, verts, faces32, labels, mus, idx))
     except torch.cuda.OutOfMemoryError:
         out["note"] = "staged breakdown skipped (out of memory)"

@@ -55,8 +55,8 @@ extern "C" {
 #define CTDR_STAT_FRAGMENTS       1 /* covered (pixel, face) pairs == the reference's `vf` (rasterizer.py:64) */
 #define CTDR_STAT_CANDIDATES      2 /* bbox (pixel, face) pairs evaluated */
 #define CTDR_STAT_LIST_SEGMENTS   3 /* extra chunk-list segments taken (0 unless > capacity chunks hit a region) */
-#define CTDR_STAT_CHUNK_VISITS    4 /* (tile, chunk) pairs whose 32 faces were staged */
-#define CTDR_STAT_CHUNK_HITS      5 /* ... of which at least one face had a candidate pixel in the tile */
+#define CTDR_STAT_FACE_BATCHES    4 /* batches of <= 32 queued faces staged in shared memory */
+#define CTDR_STAT_CHUNK_HITS      5 /* (tile, chunk) pairs in which at least one face box overlapped the tile */
 #define CTDR_STAT_COUNT           8
 
 /* geometry kinds for the vertex stage */
@@ -89,7 +89,7 @@ int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned l
  * ------------------------------------------------------------------------------------------- */
 
 /* bytes of scratch needed by ctdr_raster_forward / ctdr_raster_backward for these sizes
- * (chunk boxes; plus B*F floats used only by the deterministic backward) */
+ * (chunk and face pixel boxes; plus B*F floats used only by the deterministic backward) */
 size_t ctdr_raster_workspace_bytes(int B, int F, int H, int W);
 /* bytes of scratch needed by ctdr_raster_fragments (adds B*H*W cursors only when F > 49152) */
 size_t ctdr_raster_fragments_workspace_bytes(int B, int F, int H, int W);

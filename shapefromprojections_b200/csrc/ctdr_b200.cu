@@ -57,7 +57,8 @@ int pick_region_tiles(int B, int H, int W) {
 
 size_t raster_smem_bytes(int n_mus) { return sizeof(CtaSmem) + (size_t)n_mus * sizeof(float); }
 
-void fill_decomposition(RasterParams& P, const short4* boxes) {
+void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face_boxes) {
+    P.face_box = face_boxes;
     P.NC = (P.F + CHUNK - 1) / CHUNK;
     P.RT = pick_region_tiles(P.B, P.H, P.W);
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
@@ -65,11 +66,11 @@ void fill_decomposition(RasterParams& P, const short4* boxes) {
     P.chunk_box = boxes;
 }
 
-int launch_chunk_bbox(const RasterParams& P, short4* boxes, cudaStream_t st) {
+int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, cudaStream_t st) {
     const long long warps = (long long)P.B * P.NC;
     const long long blocks = (warps + WARPS - 1) / WARPS;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
-    k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes);
+    k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
     CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
     return 0;
 }
@@ -194,6 +195,7 @@ __global__ void k_selftest_quotient(unsigned long long per_thread, unsigned seed
 
 struct RasterWs {
     short4* boxes;
+    short4* face_boxes;
     float* fs;       // deterministic backward only
     int* cursors;    // fragment mode, multi-segment only
 };
@@ -204,6 +206,8 @@ size_t raster_ws_layout(int B, int F, int H, int W, bool want_fs, bool want_curs
     char* p = static_cast<char*>(base);
     if (out) out->boxes = reinterpret_cast<short4*>(p + off);
     off += align_up((size_t)B * NC * sizeof(short4), 256);
+    if (out) out->face_boxes = reinterpret_cast<short4*>(p + off);
+    off += align_up((size_t)B * F * sizeof(short4), 256);
     if (out) out->fs = nullptr;
     if (want_fs) {
         if (out) out->fs = reinterpret_cast<float*>(p + off);
@@ -239,8 +243,8 @@ int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream
         CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
         return 0;
     }
-    fill_decomposition(P, ws.boxes);
-    int rc = launch_chunk_bbox(P, ws.boxes, st);
+    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, st);
     if (rc) return rc;
     return launch_raster<MODE_BWD>(P, flags, st);
 }
@@ -271,18 +275,17 @@ int check_geom(int kind) {
 
 struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
-    void* raster;
-    size_t raster_bytes;
+    RasterWs rws;
     int window;   // angles per window
 };
 
 size_t project_per_angle_bytes(int F, bool bwd) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (size_t)F * (40 + (bwd ? 36 : 0)) + (size_t)NC * sizeof(short4);
+    return (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * sizeof(short4) + 512;
 }
 
 int project_ws_layout(int B, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 8 * 256;
+    const size_t slack = 10 * 256;
     const size_t per = project_per_angle_bytes(F, bwd);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -298,9 +301,7 @@ int project_ws_layout(int B, int F, int H, int W, bool bwd, void* base, size_t b
         ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
         ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
     }
-    ws->raster = p + off;
-    ws->raster_bytes = raster_ws_layout((int)win, F, H, W, false, false, nullptr, nullptr);
-    (void)H; (void)W;
+    raster_ws_layout((int)win, F, H, W, false, false, &ws->rws, p + off);
     return 0;
 }
 
@@ -364,8 +365,8 @@ int ctdr_raster_forward(const float* p6, const float* ff, const float* len3, con
     if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
     RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, stats);
     P.im = im; P.cnt = cnt;
-    fill_decomposition(P, ws.boxes);
-    if (int rc = launch_chunk_bbox(P, ws.boxes, stream)) return rc;
+    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    if (int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, stream)) return rc;
     return launch_raster<MODE_FWD>(P, flags, stream);
 }
 
@@ -382,8 +383,8 @@ int ctdr_raster_fragments(const float* p6, const float* ff, const float* len3, c
     RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, nullptr);
     P.im_in = im; P.firstidx = firstidx; P.imidx = imidx_vf; P.imwei = imwei_3vf;
     P.cnt = ws.cursors;
-    fill_decomposition(P, ws.boxes);
-    if (int rc = launch_chunk_bbox(P, ws.boxes, stream)) return rc;
+    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    if (int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, stream)) return rc;
     return launch_raster<MODE_FRAG>(P, flags, stream);
 }
 
@@ -439,7 +440,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 8 * 256;
+    return per * (size_t)win + 10 * 256;
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -463,8 +464,8 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im + (size_t)b0 * hw;
         P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
-        fill_decomposition(P, static_cast<short4*>(ws.raster));
-        if (int rc = launch_chunk_bbox(P, static_cast<short4*>(ws.raster), stream)) return rc;
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
     }
     return 0;
@@ -490,8 +491,8 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
-        fill_decomposition(P, static_cast<short4*>(ws.raster));
-        if (int rc = launch_chunk_bbox(P, static_cast<short4*>(ws.raster), stream)) return rc;
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (target) {
             P.target = target + (size_t)b0 * hw;
             P.out2 = out2;

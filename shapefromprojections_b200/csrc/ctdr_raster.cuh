@@ -8,12 +8,15 @@
 //                bounding box is precomputed by k_chunk_bbox.
 //   A CTA compacts, IN FACE ORDER, the chunks whose box overlaps its region into a shared-memory
 //   list (ballot + popc ranking); each warp then walks that list for its tile (32 boxes per
-//   ballot), stages the chunk's 32 faces in shared memory and spreads the covered bounding-box
-//   pixels ("candidates") evenly over its lanes through a prefix sum, so lane utilisation does not
-//   depend on triangle size.  Because lists, chunks and candidates are all visited in ascending
-//   face order and a tile is owned by one warp, every pixel accumulates its faces in exactly the
-//   order of the reference's per-pixel loop (diff_fp_for.cu:83) -> bit-identical sinograms, with no
-//   global atomics and one coalesced store per pixel.
+//   ballot); for every overlapping chunk the lanes test their face's precomputed pixel box against
+//   the tile and append the hits, still in face order, to a per-warp queue.  Whenever 32 faces are
+//   queued the warp stages them in shared memory (edge constants, lengths, coefficients) and
+//   spreads their covered bounding-box pixels ("candidates") evenly over its lanes through a
+//   prefix sum, so lane utilisation depends neither on triangle size nor on how many faces of a
+//   chunk touch the tile.  Because lists, chunks, queue and candidates are all visited in
+//   ascending face order and a tile is owned by one warp, every pixel accumulates its faces in
+//   exactly the order of the reference's per-pixel loop (diff_fp_for.cu:83) -> bit-identical
+//   sinograms, with no global atomics and one coalesced store per pixel.
 #pragma once
 #include "ctdr_common.cuh"
 
@@ -36,6 +39,7 @@ struct RasterParams {
     int RT;                 // tiles per region edge
     int regions_x, regions_y;
     const short4* chunk_box;  // [B,NC] pixel bbox of each chunk (x0,y0,x1,y1), empty: x0 > x1
+    const short4* face_box;   // [B,F]  pixel bbox of each face, empty when the face contributes nowhere
     // MODE_FWD outputs / MODE_STEP phat
     float* im;              // [B,H,W]
     int*   cnt;             // [B,H,W] or null
@@ -62,7 +66,7 @@ struct RasterParams {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
 k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
-             int B, int F, int H, int W, int NC, short4* __restrict__ chunk_box) {
+             int B, int F, int H, int W, int NC, short4* __restrict__ chunk_box, short4* __restrict__ face_box) {
     const long long gw = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (gw >= (long long)B * NC) return;
@@ -80,6 +84,7 @@ k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
             }
         }
     }
+    if (f < F) face_box[(long long)b * F + f] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
     x0 = __reduce_min_sync(FULL, x0); y0 = __reduce_min_sync(FULL, y0);
     x1 = __reduce_max_sync(FULL, x1); y1 = __reduce_max_sync(FULL, y1);
     if (lane == 0) chunk_box[gw] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
@@ -98,6 +103,9 @@ struct __align__(16) WarpSmem {
     // cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190).
     float4 slot[32 * SLOT_VEC];
     float mom[3][32];            // backward: sum g, sum g*k1, sum g*k2 per slot
+    // queue of faces whose box overlaps the tile, in face order (drained 32 at a time)
+    int    qface[64];
+    short4 qbox[64];
     // tile accumulators
     float acc[TILE_PIX];         // forward: running sinogram; backward: g (0 where no gradient)
     int   cntv[TILE_PIX];        // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel
@@ -187,34 +195,31 @@ struct ThreadStats {
 // one (tile, chunk): stage the chunk's faces, spread candidates over lanes, evaluate coverage
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool EXACT_DIV>
-__device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S, float* gmus,
-                                              int b, int chunk, int tx0, int ty0, int tx1, int ty1,
+__device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S, float* gmus,
+                                              int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                               int lane, ThreadStats& st) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
     constexpr bool IS_FRAG = (MODE == MODE_FRAG);
     constexpr bool IS_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
-    const int f = chunk * CHUNK + lane;
+    // lane < nb owns queued face qface[lane]; its box overlaps the tile, so it has >= 1 candidate
+    const bool mine = lane < nb;
+    const int f = mine ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
     int ncand = 0;
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1;
-    if (f < P.F) {
+    if (mine) {
+        const short4 fb = S.qbox[lane];
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
         const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
         const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
         ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
-        int ix0, iy0, ix1, iy1;
-        if (lab.x >= lab.y && face_int_bbox(ax, ay, bx, by, cx, cy, P.H, P.W, ix0, iy0, ix1, iy1)) {
-            cx0 = max(ix0, tx0); cy0 = max(iy0, ty0);
-            const int cx1 = min(ix1, tx1), cy1 = min(iy1, ty1);
-            const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
-            if (w > 0 && h > 0) { ncand = w * h; bw = w; }
-        }
+        cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
+        bw = min((int)fb.z, tx1) - cx0 + 1;
+        ncand = bw * (min((int)fb.w, ty1) - cy0 + 1);
     }
-    const unsigned nz = __ballot_sync(FULL, ncand > 0);
-    if (lane == 0) { st.visits++; st.hits += (nz != 0u); }
-    if (nz == 0u) return;
+    __syncwarp();                                       // queue entries consumed: the caller may shift it
 
     int incl = ncand;
 #pragma unroll
@@ -223,13 +228,14 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         if (lane >= d) incl += v;
     }
     const int T = __shfl_sync(FULL, incl, 31);
-    const int nslots = __popc(nz);
-    const int rank = __popc(nz & lanemask_lt());       // compacted slot of this lane's face
+    const int nslots = nb;
+    const int rank = lane;                              // queued faces are dense: slot == lane
+    if (lane == 0) { st.visits++; }
 
     // per-face constants kept in registers by the owning lane (backward epilogue)
     float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
     const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
-    if (ncand > 0) {
+    if (mine) {
         float4* sl = S.slot + rank * SLOT_VEC;
         const int box = (cx0 - tx0) | ((cy0 - ty0) << 4) | (bw << 8) |
                         (__float2int_ru(8192.0f * __frcp_rn((float)bw)) << 13);
@@ -254,7 +260,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         }
         const float ak3 = fabsf(es.k3);
         const float rd = ((ak3 > 1e-6f) & (ak3 < 1e10f)) ? __frcp_rn(es.k3) : 0.0f;
-        sl[4] = make_float4(cB, __int_as_float(incl - ncand), rd, __int_as_float(lane));
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), rd, __int_as_float(f));
         if (IS_BWD) { S.mom[0][rank] = 0.0f; S.mom[1][rank] = 0.0f; S.mom[2][rank] = 0.0f; }
     }
     __syncwarp();
@@ -356,7 +362,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
                         S.cntv[pl] = k + 1;
                         const long long pix = ((long long)b * P.H + (ty0 + py)) * P.W + (tx0 + px);
                         const long long slot = (long long)__ldg(P.firstidx + pix) + k;  // :208-209
-                        P.imidx[slot] = chunk * CHUNK + __float_as_int(v4.w) + 1;       // :212
+                        P.imidx[slot] = __float_as_int(v4.w) + 1;                      // :212
                         P.imwei[3 * slot + 0] = w0;
                         P.imwei[3 * slot + 1] = w1;
                         P.imwei[3 * slot + 2] = w2;                   // :214-216
@@ -379,7 +385,7 @@ __device__ __forceinline__ void process_chunk(const RasterParams& P, WarpSmem& S
         }
     }
 
-    if (IS_BWD && ncand > 0) {
+    if (IS_BWD && mine) {
         // per-face gradients from the moments of this tile's fragments (face_grads_from_moments)
         const float M0 = S.mom[0][rank], A1 = S.mom[1][rank], A2 = S.mom[2][rank];
         if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
@@ -596,7 +602,9 @@ k_raster(const RasterParams P) {
             }
             __syncwarp();
 
-            // walk the region's chunk list, 32 boxes per ballot, in face order
+            // walk the region's chunk list, 32 boxes per ballot, in face order; queue the faces whose
+            // own box overlaps the tile and drain the queue 32 faces at a time
+            int qn = 0;
             for (int lb = 0; lb < nlist; lb += 32) {
                 const int e = lb + lane;
                 bool hit = false;
@@ -606,10 +614,31 @@ k_raster(const RasterParams P) {
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
-                    const int chunk = __shfl_sync(FULL, cid, src);
-                    process_chunk<MODE, EXACT_DIV>(P, S, gmus, b, chunk, tx0, ty0, tx1, ty1, lane, st);
+                    const int f = __shfl_sync(FULL, cid, src) * CHUNK + lane;
+                    short4 fb = make_short4(BOX_EMPTY_LO, BOX_EMPTY_LO, -1, -1);
+                    if (f < P.F) fb = __ldg(P.face_box + (long long)b * P.F + f);
+                    const bool fh = box_overlap(fb, tx0, ty0, tx1, ty1);
+                    const unsigned hm = __ballot_sync(FULL, fh);
+                    if (lane == 0) st.hits += (hm != 0u);
+                    if (fh) {
+                        const int q = qn + __popc(hm & lanemask_lt());
+                        S.qface[q] = f; S.qbox[q] = fb;
+                    }
+                    qn += __popc(hm);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        process_batch<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
+                        const int rest = qn - 32;              // < 32: shift the tail to the front
+                        int tf = 0; short4 tb = make_short4(0, 0, 0, 0);
+                        if (lane < rest) { tf = S.qface[32 + lane]; tb = S.qbox[32 + lane]; }
+                        __syncwarp();
+                        if (lane < rest) { S.qface[lane] = tf; S.qbox[lane] = tb; }
+                        qn = rest;
+                        __syncwarp();
+                    }
                 }
             }
+            if (qn > 0) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
 
             // tile epilogue
             if (MODE == MODE_FWD) {
