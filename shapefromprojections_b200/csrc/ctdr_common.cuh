@@ -12,10 +12,10 @@ namespace ctdr {
 
 constexpr int      TILE       = 16;    // tile edge in detector pixels; one warp owns one tile
 constexpr int      TILE_PIX   = TILE * TILE;
-constexpr int      WARPS      = 8;     // warps per CTA
+constexpr int      WARPS      = 4;     // warps per CTA
 constexpr int      THREADS    = WARPS * 32;
 constexpr int      CHUNK      = 32;    // consecutive faces culled/binned together (one lane each)
-constexpr int      LIST_CAP   = 768;   // chunk-list capacity per CTA segment (>= THREADS)
+constexpr int      LIST_CAP   = 384;   // chunk-list capacity per CTA segment (>= THREADS)
 constexpr unsigned FULL       = 0xffffffffu;
 constexpr int      BOX_EMPTY_LO = 32767;
 

@@ -447,7 +447,7 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
 template <int MODE, bool EXACT_DIV>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CtaSmem& C = *reinterpret_cast<CtaSmem*>(smem_raw);
@@ -524,13 +524,20 @@ k_raster(const RasterParams P) {
                     }
                 }
             } else if (MODE == MODE_STEP) {
-                if (0.0f <= P.mask_hi) {
-                    for (int k = tid; k < rw * rh; k += THREADS) {
-                        const int y = k / rw, x = k - y * rw;
-                        const float t = __ldg(P.target + base + (long long)(ry0 + y) * P.W + rx0 + x);
-                        loss_acc += (double)t * (double)t;
-                        nvalid_acc++;
+                if (0.0f <= P.mask_hi) {        // phat == 0 everywhere here: residual = -target
+                    const bool vec = ((P.W & 3) == 0) && ((rw & 3) == 0);
+                    for (int y = warp; y < rh; y += WARPS) {
+                        const float* row = P.target + base + (long long)(ry0 + y) * P.W + rx0;
+                        if (vec) {
+                            for (int x = lane * 4; x < rw; x += 128) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(row + x));
+                                loss_acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
+                            }
+                        } else {
+                            for (int x = lane; x < rw; x += 32) { const float t = __ldg(row + x); loss_acc += (double)t * (double)t; }
+                        }
                     }
+                    if (tid == 0) nvalid_acc += (unsigned)(rw * rh);
                 }
             }
             break;
@@ -671,9 +678,9 @@ k_raster(const RasterParams P) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) loss_acc += __shfl_down_sync(FULL, loss_acc, d);
         nvalid_acc = __reduce_add_sync(FULL, nvalid_acc);
-        if (lane == 0 && nvalid_acc) {
-            atomicAdd(P.out2 + 0, loss_acc);
-            atomicAdd(P.out2 + 1, (double)nvalid_acc);
+        if (lane == 0) {
+            if (loss_acc != 0.0) atomicAdd(P.out2 + 0, loss_acc);
+            if (nvalid_acc) atomicAdd(P.out2 + 1, (double)nvalid_acc);
         }
     }
     if (P.stats) {
