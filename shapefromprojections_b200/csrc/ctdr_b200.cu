@@ -537,13 +537,34 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !target || !phat || !grad_verts || !grad_mus || !out2 || !workspace)
         return fail(CTDR_E_NULL, "ctdr_project_residual_step: null pointer");
-    // forward over all angles first (phat is an output the caller keeps), then the residual/backward sweep
-    if (int rc = ctdr_project_forward(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus,
-                                      H, W, spacing_x, spacing_y, max_sino_val, phat, nullptr,
-                                      workspace, workspace_bytes, stats, flags, stream)) return rc;
-    return project_backward_impl(geom_kind, geom, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
-                                 spacing_x, spacing_y, max_sino_val, nullptr, phat, target, out2,
-                                 grad_verts, grad_mus, workspace, workspace_bytes, stats, flags, stream);
+    // per angle window: vertex stage once, forward raster (phat is an output the caller keeps), then the
+    // residual/backward sweep over the same staged p6/len3/ff and face boxes
+    ProjectWs ws;
+    if (int rc = project_ws_layout(B, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += ws.window) {
+        const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
+        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        P.im = phat + (size_t)b0 * hw;
+        if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
+        CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
+        CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        P.im = nullptr;
+        P.im_in = phat + (size_t)b0 * hw;
+        P.target = target + (size_t)b0 * hw;
+        P.out2 = out2;
+        P.mask_hi = (float)(max_sino_val - 1e-6);
+        P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
+        P.stats = nullptr;                                   // counters describe the forward sweep only
+        if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
+        if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
+    }
+    (void)nangles;
+    return 0;
 }
 
 }  // extern "C"

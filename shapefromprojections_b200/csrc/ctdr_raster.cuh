@@ -112,8 +112,7 @@ struct __align__(16) WarpSmem {
 };
 
 struct CtaSmem {
-    int    list_id[LIST_CAP];
-    short4 list_box[LIST_CAP];
+    int    list_id[LIST_CAP];     // chunks overlapping the region, ascending (boxes are re-read through L1)
     int    wsum[WARPS];
     int    list_n;
     int    next_tile;
@@ -491,7 +490,7 @@ k_raster(const RasterParams P) {
             if (n0 + total > LIST_CAP) break;              // uniform: segment is full, resume at c later
             if (hit) {
                 const int pos = n0 + mybase + __popc(m & lanemask_lt());
-                C.list_id[pos] = ci; C.list_box[pos] = bx;
+                C.list_id[pos] = ci;
             }
             __syncthreads();
             if (tid == 0) C.list_n = n0 + total;
@@ -616,7 +615,7 @@ k_raster(const RasterParams P) {
                 const int e = lb + lane;
                 bool hit = false;
                 int cid = 0;
-                if (e < nlist) { hit = box_overlap(C.list_box[e], tx0, ty0, tx1, ty1); cid = C.list_id[e]; }
+                if (e < nlist) { cid = C.list_id[e]; hit = box_overlap(__ldg(boxes + cid), tx0, ty0, tx1, ty1); }
                 unsigned m = __ballot_sync(FULL, hit);
                 while (m) {
                     const int src = __ffs(m) - 1;

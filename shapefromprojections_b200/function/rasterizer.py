@@ -250,6 +250,62 @@ def project_residual_step(geom: GeometryDevice, verts, faces_i32, labels, mus, i
     return phat, grad_verts, grad_mus, out2
 
 
+class HostStepper:
+    """The residual step with HOST buffers in and out (mini-batch semantics of the reference loop:
+    ``p_batch = p_batch.cuda()`` from a pinned loader every iteration, ``optimize.py:157-158``).
+
+    The target sinogram is streamed host->device in angle windows on a copy stream, double
+    buffered, while the projector works on the previous window; mesh, attenuations and angle
+    indices are uploaded first; loss, valid count and gradients come back to pinned host memory.
+    """
+
+    def __init__(self, geom: GeometryDevice, faces_i32, labels, num_verts, num_mus, max_angles, windows=8):
+        dev = faces_i32.device
+        self.geom, self.faces, self.labels, self.dev = geom, faces_i32, labels, dev
+        self.win = max(1, -(-max_angles // windows))
+        self.stage = [torch.empty(self.win, geom.H, geom.W, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.phat = torch.empty(max_angles, geom.H, geom.W, dtype=torch.float32, device=dev)
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.flat = torch.zeros(3 * num_verts + num_mus, dtype=torch.float32, device=dev)
+        self.grad_verts = self.flat[:3 * num_verts].view(num_verts, 3)
+        self.grad_mus = self.flat[3 * num_verts:]
+        self.out2 = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.h_flat = torch.empty(self.flat.shape, dtype=torch.float32).pin_memory()
+        self.h_out2 = torch.empty(2, dtype=torch.float64).pin_memory()
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def step(self, h_verts, h_mus, h_idx, h_target, reduce_fn=None):
+        """All arguments are pinned host tensors; returns (h_flat, h_out2) after synchronising."""
+        dev, cur = self.dev, torch.cuda.current_stream(self.dev)
+        verts = h_verts.to(dev, non_blocking=True)
+        mus = h_mus.to(dev, non_blocking=True)
+        idx = h_idx.to(dev, non_blocking=True)
+        self.flat.zero_(); self.out2.zero_()
+        B = h_idx.numel()
+        done = [None, None]
+        for k, a in enumerate(range(0, B, self.win)):
+            n = min(self.win, B - a)
+            buf = self.stage[k & 1]
+            with torch.cuda.stream(self.copy_stream):
+                if done[k & 1] is not None:
+                    self.copy_stream.wait_event(done[k & 1])       # the buffer's previous consumer finished
+                buf[:n].copy_(h_target[a:a + n], non_blocking=True)
+                ready = torch.cuda.Event(); ready.record(self.copy_stream)
+            cur.wait_event(ready)
+            project_residual_step(self.geom, verts, self.faces, self.labels, mus, idx[a:a + n], buf[:n],
+                                  phat=self.phat[a:a + n], grad_verts=self.grad_verts, grad_mus=self.grad_mus,
+                                  out2=self.out2)
+            ev = torch.cuda.Event(); ev.record(cur); done[k & 1] = ev
+        if reduce_fn is not None:
+            reduce_fn(self.flat, self.out2)
+        self.h_flat.copy_(self.flat, non_blocking=True)
+        self.h_out2.copy_(self.out2, non_blocking=True)
+        cur.synchronize()
+        self.h2d_bytes = h_target[:B].numel() * 4 + h_verts.numel() * 4 + h_mus.numel() * 4 + h_idx.numel() * 8
+        self.d2h_bytes = self.h_flat.numel() * 4 + 16
+        return self.h_flat, self.h_out2
+
+
 class ProjectMesh(Function):
     """Fused projector: ``(verts [V,3], mus [n]) -> im [B,H,W]`` with gradients for both."""
 
