@@ -15,7 +15,7 @@ constexpr int      TILE_PIX   = TILE * TILE;
 constexpr int      WARPS      = 4;     // warps per CTA
 constexpr int      THREADS    = WARPS * 32;
 constexpr int      CHUNK      = 32;    // consecutive faces culled/binned together (one lane each)
-constexpr int      LIST_CAP   = 1024;  // chunk-list capacity per CTA segment (>= THREADS)
+constexpr int      LIST_CAP   = 512;   // chunk-list capacity per CTA segment (>= THREADS)
 constexpr unsigned FULL       = 0xffffffffu;
 constexpr int      BOX_EMPTY_LO = 32767;
 
@@ -23,6 +23,13 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// fp32 add on a shared-memory address (explicit state space: a 4-instruction CAS loop instead of
+// the generic-address atomicAdd expansion)
+__device__ __forceinline__ void shared_add(float* p, float v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
 // Integer pixel range covered by the bounding box of one projected face, with the reference's

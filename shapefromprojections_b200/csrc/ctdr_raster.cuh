@@ -102,10 +102,15 @@ struct __align__(16) WarpSmem {
     // box = lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13; excl = exclusive candidate offset of the slot;
     // cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190).
     float4 slot[32 * SLOT_VEC];
-    float mom[3][32];            // backward: sum g, sum g*k1, sum g*k2 per slot
+    union {
+        float mom[3][32];        // backward: sum g, sum g*k1, sum g*k2 per slot
+        struct {
+            unsigned hitm[TILE_PIX];         // forward: which slots of the current batch hit each pixel
+            unsigned char cpix[TILE_PIX];    // forward: pixels hit by more than one face of the batch
+        } f;
+    };
     // queue of faces whose box overlaps the tile, in face order (drained 32 at a time)
     int    qface[64];
-    short4 qbox[64];
     // tile accumulators
     float acc[TILE_PIX];         // forward: running sinogram; backward: g (0 where no gradient)
     int   cntv[TILE_PIX];        // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel
@@ -180,8 +185,8 @@ struct ThreadStats {
     int lab_in, lab_out;
     float sum_in, sum_out;
     __device__ __forceinline__ void mus_flush(float* gmus) {
-        if (sum_in != 0.0f) atomicAdd(gmus + lab_in, sum_in);
-        if (sum_out != 0.0f) atomicAdd(gmus + lab_out, sum_out);
+        if (sum_in != 0.0f) shared_add(gmus + lab_in, sum_in);
+        if (sum_out != 0.0f) shared_add(gmus + lab_out, sum_out);
         sum_in = 0.0f; sum_out = 0.0f;
     }
     __device__ __forceinline__ void mus_add(float* gmus, int li, float vi, int lo, float vo) {
@@ -209,7 +214,7 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1;
     if (mine) {
-        const short4 fb = S.qbox[lane];
+        const short4 fb = __ldg(P.face_box + bf);
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
         const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
         const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
@@ -404,6 +409,276 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
     __syncwarp();
 }
 
+
+// ------------------------------------------------------------------------------------------
+// One batch of <= 32 queued faces, forward and backward modes (the ordered candidate walk above
+// is kept for the fragment-list mode).
+//
+// Candidates (bbox-in-tile pixels of the batch, face-major) are split into 32 CONTIGUOUS ranges,
+// one per lane, so every lane walks T/32 (+-1) candidates with a plain x/y increment: perfectly
+// balanced whatever the triangle sizes, no per-step collectives, face constants re-read from the
+// staged slot (LDS.128, mostly broadcast).
+//
+// Backward: a lane sums (g, g*k1, g*k2) in registers while it stays on one face and adds them to
+// the face's shared-memory moments when it moves on.
+//
+// Forward: fragments are applied to the tile optimistically, in whatever order the lanes reach
+// them, while an 8-bit counter per pixel records how many faces of THIS batch hit it.  A pixel hit
+// by exactly one face of the batch has received exactly the reference's update
+// (acc = fma(bary, cB, fma(bary, cA, acc)), batches being processed in face order).  Pixels hit by
+// several faces of the batch (shared edges under the inclusive rule, silhouette folds) are restored
+// from a register snapshot and recomputed pixel-parallel by looping over the batch's faces in
+// ascending order — the reference's own per-pixel loop (diff_fp_for.cu:83) restricted to 32 faces.
+// The sinogram stays bit-identical.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT_DIV>
+__device__ __forceinline__ bool cover_slot(const float4 v0, const float4 v1, const float rd, const double2 dy,
+                                           float x0, float y0, float& k1, float& k2,
+                                           float& w0, float& w1, float& w2) {
+    // diff_fp_for.cu:132-151 bit for bit; prefilter and hoisted quotient as argued in cover_exact
+    const float s = __fsub_rn(x0, v0.x), t = __fsub_rn(y0, v0.y);
+    k1 = __fmaf_rn(s, v1.y, -__fmul_rn(v1.x, t));
+    k2 = __fmaf_rn(v0.z, t, -__fmul_rn(s, v0.w));
+    if (!EXACT_DIV) {
+        const float a1 = k1 * rd, a2 = k2 * rd;
+        if (fminf(a1, a2) < -1e-30f) return false;
+        if ((1.0f - a1) - a2 < -1e-4f * ((1.0f + fabsf(a1)) + fabsf(a2))) return false;
+        const double d1 = (double)k1, d2 = (double)k2;
+        const double q1 = __dmul_rn(d1, dy.y), q2 = __dmul_rn(d2, dy.y);
+        w1 = (float)(k1 == 0.0f ? q1 : __fma_rn(__fma_rn(-q1, dy.x, d1), dy.y, q1));
+        w2 = (float)(k2 == 0.0f ? q2 : __fma_rn(__fma_rn(-q2, dy.x, d2), dy.y, q2));
+    } else {
+        w1 = (float)((double)k1 / dy.x);
+        w2 = (float)((double)k2 / dy.x);
+    }
+    w0 = __fsub_rn(__fsub_rn(1.0f, w1), w2);
+    return !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
+}
+
+template <int MODE, bool EXACT_DIV>
+__device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
+                                                      int b, int nb, int tx0, int ty0, int tx1, int ty1,
+                                                      int lane, ThreadStats& st) {
+    constexpr bool IS_FWD = (MODE == MODE_FWD);
+    const bool mine = lane < nb;
+    const int f = mine ? S.qface[lane] : 0;
+    const long long bf = (long long)b * P.F + f;
+    int ncand = 0;
+    int2 lab = make_int2(0, 0);
+    float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+    int cx0 = 0, cy0 = 0, bw = 1, bh = 1;
+    if (mine) {
+        const short4 fb = __ldg(P.face_box + bf);
+        lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
+        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
+        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+        cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
+        bw = min((int)fb.z, tx1) - cx0 + 1;
+        bh = min((int)fb.w, ty1) - cy0 + 1;
+        ncand = bw * bh;
+    }
+    __syncwarp();                                       // queue entries consumed
+
+    int incl = ncand;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int T = __shfl_sync(FULL, incl, 31);
+    if (lane == 0) st.visits++;
+
+    float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
+    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+    if (mine) {
+        float4* sl = S.slot + lane * SLOT_VEC;
+        const int box = (cx0 - tx0) | ((cy0 - ty0) << 4) | (bw << 8) | (bh << 13);
+        sl[0] = make_float4(es.ax, es.ay, es.m, es.p);
+        sl[1] = make_float4(es.n, es.q, es.k3, __int_as_float(box));
+        const double d = (double)es.k3 + 1e-15;                        // diff_fp_for.cu:144 denominator
+        reinterpret_cast<double2*>(sl)[2] = make_double2(d, 1.0 / d);
+        const float* pl = P.len3 + bf * 3;
+        r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
+        if (__ldg(P.ff + bf) < 0.0f) sgn = -1.0f;                     // diff_fp_for.cu:94-96
+        if (lab.x == lab.y) sgn = -sgn;                               // :167-169
+        float cA = 0.0f, cB = 0.0f;
+        if (IS_FWD) {
+            const float mu_in = __ldg(P.mus + lab.x);
+            float mu_out = __ldg(P.mus + lab.y);
+            if (lab.y == 0) mu_out = -mu_out;                         // :174-175
+            cA = __fmul_rn(sgn, mu_in);                               // :187
+            cB = -__fmul_rn(sgn, mu_out);                             // :190
+            sl[3] = make_float4(r0, r1, r2, cA);
+        } else {
+            S.mom[0][lane] = 0.0f; S.mom[1][lane] = 0.0f; S.mom[2][lane] = 0.0f;
+        }
+        const float ak3 = fabsf(es.k3);
+        const float rd = ((ak3 > 1e-6f) & (ak3 < 1e10f)) ? __frcp_rn(es.k3) : 0.0f;
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), rd, __int_as_float(f));
+    }
+    // forward: snapshot of the 8 pixels this lane checks afterwards (4*lane.. and 128+4*lane..)
+    float4 old0 = make_float4(0, 0, 0, 0), old1 = old0;
+    if (IS_FWD) {
+        old0 = *reinterpret_cast<const float4*>(S.acc + 4 * lane);
+        old1 = *reinterpret_cast<const float4*>(S.acc + 128 + 4 * lane);
+    }
+    __syncwarp();
+
+    // ---- contiguous candidate range of this lane --------------------------------------------
+    const int q = T >> 5, rem = T & 31;
+    const int mycount = q + (lane < rem ? 1 : 0);
+    const int j0 = lane * q + min(lane, rem);
+    const int iters = q + (rem ? 1 : 0);
+    int i = 0;                                           // slot owning candidate j0: last slot with excl <= j0
+    if (mycount > 0) {
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int c = i + step;
+            if (c < nb && __float_as_int(S.slot[c * SLOT_VEC + 4].y) <= j0) i = c;
+        }
+    }
+    int lx = 0, ly = 0, e = 0;
+    {
+        const float4 v1 = S.slot[i * SLOT_VEC + 1];
+        const int box = __float_as_int(v1.w);
+        const int w = (box >> 8) & 31;
+        e = j0 - __float_as_int(S.slot[i * SLOT_VEC + 4].y);
+        ly = (int)__fdividef((float)e + 0.5f, (float)w);
+        lx = e - ly * w;
+    }
+    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
+    bool whole = (e == 0);                               // current face entered at its first candidate
+
+    for (int t = 0; t < iters; ++t) {
+        const bool act = t < mycount;
+        const float4* sl = S.slot + i * SLOT_VEC;
+        const float4 v0 = sl[0], v1 = sl[1], v4 = sl[4];
+        const int box = __float_as_int(v1.w);
+        const int w = (box >> 8) & 31, n_i = w * ((box >> 13) & 31);
+        const int px = (box & 15) + lx, py = ((box >> 4) & 15) + ly;
+        const int pl = (py * TILE + px) & (TILE_PIX - 1);
+        bool in = false;
+        float k1 = 0.0f, k2 = 0.0f, w0, w1, w2;
+        if (act) {
+            in = cover_slot<EXACT_DIV>(v0, v1, v4.z, reinterpret_cast<const double2*>(sl)[2],
+                                       (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
+            st.cand++;
+        }
+        if (IS_FWD) {
+            if (in) {
+                const float4 v3 = sl[3];
+                const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));  // :182
+                if (!(bary > 0.0f)) st.nonpos++;                      // :183 assert -> counter
+                st.frag++;
+                atomicOr(&S.f.hitm[pl], 1u << i);
+                S.acc[pl] = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, S.acc[pl]));             // :187,190
+            }
+        } else {
+            if (in) {
+                const float g = S.acc[pl];
+                if (g != 0.0f) { st.frag++; M0 += g; A1 = fmaf(g, k1, A1); A2 = fmaf(g, k2, A2); }
+            }
+        }
+        if (act) {                                       // advance inside the face, or move to the next one
+            ++e; ++lx;
+            if (lx == w) { lx = 0; ++ly; }
+            if (e == n_i) {
+                if (!IS_FWD) {
+                    if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
+                        if (whole) {           // entered at its first candidate and finished here: sole contributor
+                            S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
+                        } else {
+                            shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
+                        }
+                    }
+                    M0 = 0.0f; A1 = 0.0f; A2 = 0.0f;
+                    whole = true;
+                }
+                i = min(i + 1, nb - 1); e = 0; lx = 0; ly = 0;
+            }
+        }
+    }
+    if (!IS_FWD && (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f)) {   // face shared with the following lanes
+        shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
+    }
+    __syncwarp();
+
+    if (IS_FWD) {
+        // ---- pixels hit by several faces of this batch: restore and redo them in face order --------
+        const uint4 h0 = *reinterpret_cast<const uint4*>(S.f.hitm + 4 * lane);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(S.f.hitm + 128 + 4 * lane);
+        *reinterpret_cast<uint4*>(S.f.hitm + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(S.f.hitm + 128 + 4 * lane) = make_uint4(0u, 0u, 0u, 0u);
+        int ncp = 0;
+        const unsigned hm[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float ov[8] = {old0.x, old0.y, old0.z, old0.w, old1.x, old1.y, old1.z, old1.w};
+        unsigned mymask[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int pix = (k < 4 ? 0 : 128) + 4 * lane + (k & 3);
+            if (P.cnt && hm[k]) S.cntv[pix] += __popc(hm[k]);         // :192
+            const bool multi = (hm[k] & (hm[k] - 1u)) != 0u;          // more than one face of the batch
+            mymask[k] = multi ? hm[k] : 0u;
+            const unsigned m = __ballot_sync(FULL, multi);
+            if (m) {
+                if (multi) {
+                    S.acc[pix] = ov[k];
+                    S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)pix;
+                }
+                ncp += __popc(m);
+            }
+        }
+        if (ncp) {
+            // the hit masks of the conflicted pixels go back to shared memory for their new owners
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (mymask[k]) S.f.hitm[(k < 4 ? 0 : 128) + 4 * lane + (k & 3)] = mymask[k];
+            __syncwarp();
+            for (int base = 0; base < ncp; base += 32) {
+                const bool have = base + lane < ncp;
+                const int pix = have ? (int)S.f.cpix[base + lane] : 0;
+                const int px = pix & 15, py = pix >> 4;
+                float acc = S.acc[pix];
+                unsigned fm = have ? S.f.hitm[pix] : 0u;
+                while (fm) {                                          // ascending face id (diff_fp_for.cu:83)
+                    const int fi = __ffs(fm) - 1;
+                    fm &= fm - 1u;
+                    const float4* sl = S.slot + fi * SLOT_VEC;
+                    const float4 v0 = sl[0], v1 = sl[1], v3 = sl[3], v4 = sl[4];
+                    float k1, k2, w0, w1, w2;
+                    // the face is known to cover the pixel: only the weights are needed again
+                    cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
+                                          (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
+                    const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));
+                    acc = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, acc));
+                }
+                if (have) { S.acc[pix] = acc; S.f.hitm[pix] = 0u; }
+            }
+        }
+        __syncwarp();
+        return;
+    }
+
+    if (mine) {
+        // per-face gradients from the moments of this tile's fragments (face_grads_from_moments)
+        const float m0 = S.mom[0][lane], a1 = S.mom[1][lane], a2 = S.mom[2][lane];
+        if (m0 != 0.0f || a1 != 0.0f || a2 != 0.0f) {
+            const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
+            const float cgeo = sgn * (mu_in - mu_out);                // raw mu, no label-0 flip (back.cu:115)
+            float gp[6], gl[3], bsum;
+            face_grads_from_moments(es, r0, r1, r2, cgeo, m0, a1, a2, gp, gl, bsum);
+            float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
+            atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
+            st.mus_add(gmus, lab.x, (lab.x == 0 ? -sgn : sgn) * bsum, lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
+            float* dp = P.grad_p6 + bf * 6;                           // back.cu:285-292
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // tile load / store helpers (one warp, 16x16 pixels, rows of 64 B)
 // ------------------------------------------------------------------------------------------
@@ -555,6 +830,8 @@ k_raster(const RasterParams P) {
 
             // tile prologue
             if (MODE == MODE_FWD) {
+#pragma unroll
+                for (int k = 0; k < TILE_PIX / 32; ++k) S.f.hitm[lane + 32 * k] = 0u;
                 if (first) {
 #pragma unroll
                     for (int k = 0; k < TILE_PIX / 32; ++k) { S.acc[lane + 32 * k] = 0.0f; S.cntv[lane + 32 * k] = 0; }
@@ -592,18 +869,24 @@ k_raster(const RasterParams P) {
                 // gradient predicate, diff_fp_for.cu:69-73); loss and count once per tile
                 const long long base = (long long)b * P.H * P.W;
                 const int col = lane & 15, r = lane >> 4;
-                for (int row = r; row < TILE; row += 2) {
+                float vv[TILE / 2], tt[TILE / 2];
+#pragma unroll
+                for (int k = 0; k < TILE / 2; ++k) {          // all 16 loads in flight before any use
+                    const int row = r + 2 * k;
+                    const bool ok = (ty0 + row <= ty1) && (tx0 + col <= tx1);
+                    const long long o = base + (long long)(ty0 + row) * P.W + tx0 + col;
+                    vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
+                    tt[k] = ok ? __ldg(P.target + o) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < TILE / 2; ++k) {
                     float g = 0.0f;
-                    if (ty0 + row <= ty1 && tx0 + col <= tx1) {
-                        const long long o = base + (long long)(ty0 + row) * P.W + tx0 + col;
-                        const float v = __ldg(P.im_in + o);
-                        if (v > -1e-6f && v <= P.mask_hi) {
-                            const float diff = v - __ldg(P.target + o);
-                            g = 2.0f * diff;
-                            if (first) { loss_acc += (double)diff * (double)diff; nvalid_acc++; }
-                        }
+                    if (vv[k] > -1e-6f && vv[k] <= P.mask_hi) {
+                        const float diff = vv[k] - tt[k];
+                        g = 2.0f * diff;
+                        if (first) { loss_acc += (double)diff * (double)diff; nvalid_acc++; }
                     }
-                    S.acc[row * TILE + col] = g;
+                    S.acc[(r + 2 * k) * TILE + col] = g;
                 }
             }
             __syncwarp();
@@ -628,23 +911,27 @@ k_raster(const RasterParams P) {
                     if (lane == 0) st.hits += (hm != 0u);
                     if (fh) {
                         const int q = qn + __popc(hm & lanemask_lt());
-                        S.qface[q] = f; S.qbox[q] = fb;
+                        S.qface[q] = f;
                     }
                     qn += __popc(hm);
                     __syncwarp();
                     if (qn >= 32) {
-                        process_batch<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
+                        if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
+                        else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
                         const int rest = qn - 32;              // < 32: shift the tail to the front
-                        int tf = 0; short4 tb = make_short4(0, 0, 0, 0);
-                        if (lane < rest) { tf = S.qface[32 + lane]; tb = S.qbox[32 + lane]; }
+                        int tf = 0;
+                        if (lane < rest) tf = S.qface[32 + lane];
                         __syncwarp();
-                        if (lane < rest) { S.qface[lane] = tf; S.qbox[lane] = tb; }
+                        if (lane < rest) S.qface[lane] = tf;
                         qn = rest;
                         __syncwarp();
                     }
                 }
             }
-            if (qn > 0) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
+            if (qn > 0) {
+                if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
+                else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
+            }
 
             // tile epilogue
             if (MODE == MODE_FWD) {
