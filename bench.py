@@ -180,14 +180,15 @@ def main():
     wl = workloads.make_workload(args.config)
     H, W, NA = wl["H"], wl["W"], wl["nangles"]
     V, F = wl["verts"].shape[0], wl["faces"].shape[0]
-    b0, b1 = distributed.shard_angles(NA, rank, world)
-    Bl = b1 - b0
+    emu = int(os.environ.get("CTDR_BENCH_EMULATE_WORLD", "0"))    # profiling aid: one rank's shard of an N-way split
+    my_angles = distributed.strided_angles(NA, rank if not emu else 0, world if not emu else emu)
+    Bl = int(my_angles.numel())
     gd = R.GeometryDevice(wl["geom"], dev)
     verts = torch.as_tensor(wl["verts"]).to(dev)
     faces32 = torch.as_tensor(wl["faces"]).to(torch.int32).to(dev)
     labels = torch.as_tensor(wl["labels"]).to(dev)
     mus = torch.as_tensor(wl["mus"]).to(dev)
-    idx = torch.arange(b0, b1, device=dev, dtype=torch.int64)
+    idx = my_angles.to(dev)
 
     # seeded target: projection of the ground-truth shape (the mesh scaled anisotropically)
     gt = verts * torch.as_tensor(workloads.TARGET_SCALE).to(dev)
@@ -233,7 +234,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_verts = wl_pin(torch, wl["verts"]); h_mus = wl_pin(torch, wl["mus"])
-        h_idx = torch.arange(b0, b1, dtype=torch.int64).pin_memory()
+        h_idx = my_angles.clone().pin_memory()
         h_target = torch.empty(target.shape, dtype=torch.float32).pin_memory()
         h_target.copy_(target)
         stepper = R.HostStepper(gd, faces32, labels, V, mus.numel(), Bl, windows=8)
@@ -308,7 +309,7 @@ def main():
             "config": {"workload": f"{args.config}: {wl['desc']}", "angles_per_gpu": Bl, "V": V, "F": F,
                        "step": "projection + masked-L2 residual + backward over all angles + gradient all-reduce",
                        "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)",
-                       "parallelism": f"angles sharded over {world} GPU(s), mesh replicated"},
+                       "parallelism": f"angles sharded over {world} GPU(s) (rank r owns angles r, r+N, ...), mesh replicated"},
             "roofline": roofline, "clocks": clocks, "gpu_launches": LAUNCHES_PER_STEP * args.steps,
             "loss": loss_sum / max(n_valid, 1.0), "n_valid": n_valid}
     if e2e is not None:

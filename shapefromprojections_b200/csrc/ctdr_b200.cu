@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 using namespace ctdr;
 
@@ -44,26 +45,37 @@ int check_sizes(int B, int F, int H, int W, int n_mus) {
     return 0;
 }
 
-int pick_region_tiles(int B, int H, int W) {
-    // one CTA per region of RT x RT tiles; shrink regions until the grid fills the 148 SMs a few times
-    int rt = 8;
-    while (rt > 2) {
-        const long long regions = (long long)((W + rt * TILE - 1) / (rt * TILE)) * ((H + rt * TILE - 1) / (rt * TILE));
-        if (regions * B >= 4LL * 148) break;
-        rt >>= 1;
+int pick_region_tiles(int B, int F, int H, int W) {
+    if (const char* env = getenv("CTDR_REGION_TILES")) {      // tuning/debug override: 2, 4 or 8
+        const int v = atoi(env);
+        if (v == 2 || v == 4 || v == 8) return v;
     }
+    // One CTA per region of RT x RT tiles.  8x8 amortises the per-CTA list build best; 4x4 gives four
+    // times more CTAs, which wins when the grid is small (multi-GPU angle shards: tail effect) or when
+    // region lists are long (very fine meshes: fewer list segments).  Measured on config 3 / north star.
+    int rt = 8;
+    const long long regions8 = (long long)((W + 8 * TILE - 1) / (8 * TILE)) * ((H + 8 * TILE - 1) / (8 * TILE));
+    if (regions8 * B < 64LL * 148 || F > 300000) rt = 4;
+    const long long regions4 = (long long)((W + 4 * TILE - 1) / (4 * TILE)) * ((H + 4 * TILE - 1) / (4 * TILE));
+    if (regions4 * B < 2LL * 148) rt = 2;
     return rt;
 }
 
 size_t raster_smem_bytes(int n_mus) { return sizeof(CtaSmem) + (size_t)n_mus * sizeof(float); }
 
-void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face_boxes) {
-    P.face_box = face_boxes;
+constexpr int MAX_SR = 4;   // super-regions per detector edge
+
+void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face_boxes, const int* slist, const int* scount) {
+    P.face_box = face_boxes; P.slist = slist; P.scount = scount;
     P.NC = (P.F + CHUNK - 1) / CHUNK;
-    P.RT = pick_region_tiles(P.B, P.H, P.W);
+    P.RT = pick_region_tiles(P.B, P.F, P.H, P.W);
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
     P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
     P.chunk_box = boxes;
+    P.sr_rx = (P.regions_x + MAX_SR - 1) / MAX_SR;
+    P.sr_ry = (P.regions_y + MAX_SR - 1) / MAX_SR;
+    P.nsr_x = (P.regions_x + P.sr_rx - 1) / P.sr_rx;
+    P.nsr_y = (P.regions_y + P.sr_ry - 1) / P.sr_ry;
 }
 
 int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, cudaStream_t st) {
@@ -72,6 +84,14 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
     k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
     CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
+    if (P.slist) {      // tile-binned modes: coarse (super-region) lists for phase A of k_raster
+        const long long sblocks = (long long)P.B * P.nsr_x * P.nsr_y;
+        if (sblocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B too large for one launch");
+        k_super_lists<<<(unsigned)sblocks, THREADS, 0, st>>>(boxes, P.NC, P.H, P.W, P.nsr_x, P.nsr_y,
+                                                             P.sr_rx * P.RT * TILE, P.sr_ry * P.RT * TILE,
+                                                             const_cast<int*>(P.slist), const_cast<int*>(P.scount));
+        CTDR_CUDA(cudaGetLastError(), "k_super_lists launch");
+    }
     return 0;
 }
 
@@ -196,6 +216,8 @@ __global__ void k_selftest_quotient(unsigned long long per_thread, unsigned seed
 struct RasterWs {
     short4* boxes;
     short4* face_boxes;
+    int* slist;
+    int* scount;
     float* fs;       // deterministic backward only
     int* cursors;    // fragment mode, multi-segment only
 };
@@ -208,6 +230,10 @@ size_t raster_ws_layout(int B, int F, int H, int W, bool want_fs, bool want_curs
     off += align_up((size_t)B * NC * sizeof(short4), 256);
     if (out) out->face_boxes = reinterpret_cast<short4*>(p + off);
     off += align_up((size_t)B * F * sizeof(short4), 256);
+    if (out) out->slist = reinterpret_cast<int*>(p + off);
+    off += align_up((size_t)B * MAX_SR * MAX_SR * NC * sizeof(int), 256);
+    if (out) out->scount = reinterpret_cast<int*>(p + off);
+    off += align_up((size_t)B * MAX_SR * MAX_SR * sizeof(int), 256);
     if (out) out->fs = nullptr;
     if (want_fs) {
         if (out) out->fs = reinterpret_cast<float*>(p + off);
@@ -243,7 +269,7 @@ int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream
         CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
         return 0;
     }
-    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    fill_decomposition(P, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
     int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, st);
     if (rc) return rc;
     return launch_raster<MODE_BWD>(P, flags, st);
@@ -281,11 +307,12 @@ struct ProjectWs {
 
 size_t project_per_angle_bytes(int F, bool bwd) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * sizeof(short4) + 512;
+    return (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+           MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
 int project_ws_layout(int B, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 10 * 256;
+    const size_t slack = 14 * 256;
     const size_t per = project_per_angle_bytes(F, bwd);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -365,7 +392,7 @@ int ctdr_raster_forward(const float* p6, const float* ff, const float* len3, con
     if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
     RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, stats);
     P.im = im; P.cnt = cnt;
-    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    fill_decomposition(P, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
     if (int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, stream)) return rc;
     return launch_raster<MODE_FWD>(P, flags, stream);
 }
@@ -383,7 +410,7 @@ int ctdr_raster_fragments(const float* p6, const float* ff, const float* len3, c
     RasterParams P = base_params(p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, nullptr);
     P.im_in = im; P.firstidx = firstidx; P.imidx = imidx_vf; P.imwei = imwei_3vf;
     P.cnt = ws.cursors;
-    fill_decomposition(P, ws.boxes, ws.face_boxes);
+    fill_decomposition(P, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
     if (int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, stream)) return rc;
     return launch_raster<MODE_FRAG>(P, flags, stream);
 }
@@ -440,7 +467,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 10 * 256;
+    return per * (size_t)win + 14 * 256;
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -464,7 +491,7 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im + (size_t)b0 * hw;
         P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
-        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
     }
@@ -491,7 +518,7 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
-        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (target) {
             P.target = target + (size_t)b0 * hw;
@@ -547,7 +574,7 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
-        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes);
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         P.im = phat + (size_t)b0 * hw;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;

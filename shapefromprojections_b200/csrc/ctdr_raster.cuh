@@ -40,6 +40,11 @@ struct RasterParams {
     int regions_x, regions_y;
     const short4* chunk_box;  // [B,NC] pixel bbox of each chunk (x0,y0,x1,y1), empty: x0 > x1
     const short4* face_box;   // [B,F]  pixel bbox of each face, empty when the face contributes nowhere
+    // coarse level: per (angle, super-region) ordered list of the chunks overlapping it
+    const int* slist;         // [B, nsr, NC]
+    const int* scount;        // [B, nsr]
+    int nsr_x, nsr_y;         // super-regions per detector edge (<= 4 x 4)
+    int sr_rx, sr_ry;         // regions per super-region edge
     // MODE_FWD outputs / MODE_STEP phat
     float* im;              // [B,H,W]
     int*   cnt;             // [B,H,W] or null
@@ -88,6 +93,43 @@ k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
     x0 = __reduce_min_sync(FULL, x0); y0 = __reduce_min_sync(FULL, y0);
     x1 = __reduce_max_sync(FULL, x1); y1 = __reduce_max_sync(FULL, y1);
     if (lane == 0) chunk_box[gw] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+}
+
+// ------------------------------------------------------------------------------------------
+// coarse binning: one CTA per (angle, super-region) compacts, in face order, the chunks whose box
+// overlaps the super-region (<= 4 x 4 super-regions per detector, so every chunk box is read 16
+// times instead of once per region)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+k_super_lists(const short4* __restrict__ chunk_box, int NC, int H, int W, int nsr_x, int nsr_y,
+              int sr_w, int sr_h, int* __restrict__ slist, int* __restrict__ scount) {
+    __shared__ int wsum[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsr = nsr_x * nsr_y;
+    const int b = blockIdx.x / nsr, sr = blockIdx.x % nsr;
+    const int x0 = (sr % nsr_x) * sr_w, y0 = (sr / nsr_x) * sr_h;
+    const int x1 = min(x0 + sr_w, W) - 1, y1 = min(y0 + sr_h, H) - 1;
+    const short4* boxes = chunk_box + (long long)b * NC;
+    int* out = slist + ((long long)b * nsr + sr) * NC;
+    int n = 0;
+    for (int c = 0; c < NC; c += THREADS) {
+        const int ci = c + tid;
+        bool hit = false;
+        if (ci < NC) {
+            const short4 bx = __ldg(boxes + ci);
+            hit = (bx.x <= x1) & (bx.z >= x0) & (bx.y <= y1) & (bx.w >= y0);
+        }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int total = 0, mybase = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { const int v = wsum[w]; if (w < warp) mybase += v; total += v; }
+        if (hit) out[n + mybase + __popc(m & lanemask_lt())] = ci;
+        n += total;
+        __syncthreads();
+    }
+    if (tid == 0) scount[(long long)b * nsr + sr] = n;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,7 +334,6 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
         const float s = __fsub_rn((float)(tx0 + px), v0.x), t = __fsub_rn((float)(ty0 + py), v0.y);
         const float k1 = __fmaf_rn(s, v1.y, -__fmul_rn(v1.x, t));
         const float k2 = __fmaf_rn(v0.z, t, -__fmul_rn(s, v0.w));
-        const float k3 = v1.z;
         bool in = act;
         if (!EXACT_DIV) {
             // Prefilter (see cover_exact in ctdr_common.cuh for the argument): v4.z = 1/k3, or 0 when
@@ -734,6 +775,10 @@ k_raster(const RasterParams P) {
     const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
     const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
     const short4* boxes = P.chunk_box + (long long)b * P.NC;
+    const int srx = (rr % P.regions_x) / P.sr_rx, sry = (rr / P.regions_x) / P.sr_ry;
+    const long long sidx = (long long)b * (P.nsr_x * P.nsr_y) + sry * P.nsr_x + srx;
+    const int* super = P.slist + sidx * P.NC;
+    const int nsuper = __ldg(P.scount + sidx);
     WarpSmem& S = C.warp[warp];
     ThreadStats st = {0u, 0u, 0u, 0u, 0u, 0, 0, 0.0f, 0.0f};
 
@@ -750,11 +795,11 @@ k_raster(const RasterParams P) {
         // ---- phase A: ordered compaction of the chunks overlapping this region -------------
         if (tid == 0) { C.list_n = 0; C.next_tile = 0; }
         __syncthreads();
-        while (c < P.NC) {
-            const int ci = c + tid;
+        while (c < nsuper) {
+            const int cpos = c + tid;
             bool hit = false;
-            short4 bx = make_short4(0, 0, 0, 0);
-            if (ci < P.NC) { bx = __ldg(boxes + ci); hit = box_overlap(bx, rx0, ry0, rx1, ry1); }
+            int ci = 0;
+            if (cpos < nsuper) { ci = __ldg(super + cpos); hit = box_overlap(__ldg(boxes + ci), rx0, ry0, rx1, ry1); }
             const unsigned m = __ballot_sync(FULL, hit);
             if (lane == 0) C.wsum[warp] = __popc(m);
             __syncthreads();
@@ -773,7 +818,7 @@ k_raster(const RasterParams P) {
         }
         __syncthreads();
         const int nlist = C.list_n;
-        const bool first = (seg == 0), last = (c >= P.NC);
+        const bool first = (seg == 0), last = (c >= nsuper);
 
         if (nlist == 0 && first && last) {
             // nothing projects into this region: zero-fill (forward); the residual step still owes
@@ -949,7 +994,7 @@ k_raster(const RasterParams P) {
         }
         __syncthreads();
         ++seg;
-    } while (c < P.NC);
+    } while (c < nsuper);
 
     if (K_BWD) {
         st.mus_flush(gmus);

@@ -29,6 +29,16 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local_rank
 
 
+def strided_angles(nangles: int, rank: int, world: int):
+    """Angles ``rank, rank+world, ...``: every rank sees the whole orbit, so the per-angle cost
+    variation (edge-on views carry fewer fragments than face-on ones) averages out; contiguous
+    blocks were up to ~20 % imbalanced on the torus workload."""
+    import torch
+    if rank >= nangles:
+        return torch.zeros(0, dtype=torch.int64)
+    return torch.arange(rank, nangles, world, dtype=torch.int64)
+
+
 def shard_angles(nangles: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block [begin, end) of rank ``rank``; block sizes differ by at most one angle."""
     base, rem = divmod(nangles, world)

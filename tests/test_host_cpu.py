@@ -104,6 +104,8 @@ def test_angle_sharding_is_a_partition():
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+        strided = [distributed.strided_angles(n, r, w).tolist() for r in range(w)]
+        assert sorted(a for part in strided for a in part) == list(range(n))
 
 
 _GLOO_WORKER = r"""
