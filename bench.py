@@ -317,11 +317,21 @@ def main():
     if breakdown is not None:
         line["kernels"] = breakdown
         if "raster_step_ms" in breakdown:
-            k_bytes = 8 * Bl * H * W      # read phat + read target (the kernel's own algorithmic bytes)
+            k_bytes = 8 * Bl * H * W      # the kernel's own algorithmic bytes: 4 B phat + 4 B target/gradient per pixel
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tj = json.load(fh).get(args.config)
+                if tj and tj.get("angles") == Bl:
+                    traffic = tj.get("k_raster<MODE_STEP>")
+            line["roofline"]["traffic"] = traffic
             line["roofline"]["dominant_kernel"] = {
-                "name": "k_raster<MODE_STEP>", "ms": breakdown["raster_step_ms"],
+                "name": "k_raster<MODE_STEP> (residual + backward sweep; timed as the staged MODE_BWD launch, same traversal)",
+                "ms": breakdown["raster_step_ms"], "algorithmic_bytes": k_bytes,
                 "achieved": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9, "unit": "GB/s",
-                "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak}
+                "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ncu_cfg3_summary.md)"}
     if not args.no_cpu_baseline and world == 1:
         gpix, dt, sample = cpu_reference_sample(wl)
         line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": os.cpu_count(), "kind": "port",
