@@ -345,7 +345,7 @@ int launch_vertex_backward(const VertexParams& P, const float* gp6, const float*
     // enough angle slices to fill the machine, few enough to keep atomics per vertex low
     int slices = 1;
     const long long face_blocks = (P.F + 255) / 256;
-    while (slices < P.B && face_blocks * slices < 4 * 148 && slices < 64) slices <<= 1;
+    while (slices < P.B && face_blocks * slices < 24 * 148 && slices < 64) slices <<= 1;
     if (slices > P.B) slices = P.B;
     const int per = (P.B + slices - 1) / slices;
     dim3 grid((unsigned)face_blocks, (unsigned)((P.B + per - 1) / per));

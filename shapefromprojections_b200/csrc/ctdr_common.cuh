@@ -15,7 +15,7 @@ constexpr int      TILE_PIX   = TILE * TILE;
 constexpr int      WARPS      = 4;     // warps per CTA
 constexpr int      THREADS    = WARPS * 32;
 constexpr int      CHUNK      = 32;    // consecutive faces culled/binned together (one lane each)
-constexpr int      LIST_CAP   = 512;   // chunk-list capacity per CTA segment (>= THREADS)
+constexpr int      LIST_CAP   = 320;   // chunk-list capacity per CTA segment (>= THREADS)
 constexpr unsigned FULL       = 0xffffffffu;
 constexpr int      BOX_EMPTY_LO = 32767;
 

@@ -144,6 +144,9 @@ struct __align__(16) WarpSmem {
     // box = lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13; excl = exclusive candidate offset of the slot;
     // cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190).
     float4 slot[32 * SLOT_VEC];
+    // Per-row pixel spans of the staged faces inside the tile: one byte per (slot, row) =
+    // first column << 4 | last column (tile-relative); first > last marks an empty row.
+    unsigned char span[32][TILE];
     union {
         float mom[3][32];        // backward: sum g, sum g*k1, sum g*k2 per slot
         struct {
@@ -496,19 +499,98 @@ __device__ __forceinline__ bool cover_slot(const float4 v0, const float4 v1, con
     return !(w0 < 0.0f || w1 < 0.0f || w2 < 0.0f);
 }
 
+// Pixels hit by several faces of the current batch: recompute them over exactly the faces in their
+// hit mask, in ascending face order (kept out of line: rare, and it keeps the hot loop's code small).
+template <bool EXACT_DIV>
+__device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int ty0, int lane) {
+#pragma unroll 1
+    for (int base = 0; base < ncp; base += 32) {
+        const bool have = base + lane < ncp;
+        const int pix = have ? (int)S.f.cpix[base + lane] : 0;
+        const int px = pix & 15, py = pix >> 4;
+        float acc = S.acc[pix];
+        unsigned fm = have ? S.f.hitm[pix] : 0u;
+#pragma unroll 1
+        while (fm) {                                          // ascending face id (diff_fp_for.cu:83)
+            const int fi = __ffs(fm) - 1;
+            fm &= fm - 1u;
+            const float4* sl = S.slot + fi * SLOT_VEC;
+            const float4 v0 = sl[0], v1 = sl[1], v3 = sl[3], v4 = sl[4];
+            float k1, k2, w0, w1, w2;
+            // the face is known to cover the pixel: only the weights are needed again
+            cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
+                                  (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
+            const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));
+            acc = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, acc));
+        }
+        if (have) { S.acc[pix] = acc; S.f.hitm[pix] = 0u; }
+    }
+}
+
+// Conservative column range of one face on one detector row (absolute pixels, clipped to [x_lo, x_hi]).
+// Inside <=> sg*k1 >= 0, sg*k2 >= 0, sg*(k1+k2) <= |d| with sg = sign(d) (diff_fp_for.cu:140-151);
+// for a fixed row each is a linear inequality a*s + b(t) >= 0 in s = x - ax with b linear in
+// t = y - ay, so the root -b/a is R*t + C with per-face R, C.  Bounds are widened by a margin that
+// dominates the rounding of the reference's own k1/k2/w0 evaluation (and of this estimate), so
+// every pixel the reference counts lies inside the range; the exact test still decides.
+// Near-zero slopes give no bound.
+struct SpanSetup {
+    float R[3], C[3], M0[3], M1[3];     // root_j = R*t + C ; margin_j = M0 + M1*|t|
+    float lower[3];                     // +1: lower bound on s (a_j > 0), -1: upper bound, 0: unused
+};
+
+__device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es) {
+    SpanSetup sp;
+    const float sg = es.k3 < 0.0f ? -1.0f : 1.0f;
+    // a_j*s + beta_j*t + gamma_j >= 0
+    const float a[3] = {sg * es.q, -sg * es.p, -sg * (es.q - es.p)};
+    const float beta[3] = {-sg * es.n, sg * es.m, -sg * (es.m - es.n)};
+    const float gamma[3] = {0.0f, 0.0f, fabsf(es.k3)};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const bool use = fabsf(a[j]) > 1e-4f;
+        const float ia = use ? __frcp_rn(a[j]) : 0.0f;
+        sp.R[j] = -beta[j] * ia;
+        sp.C[j] = -gamma[j] * ia;
+        // rounding of the reference's k1/k2/w0 (~2^-23 of the products involved) and of this estimate
+        // (a few ulp of |root| <= |R||t| + |C|), with a 10x factor, plus 0.02 px
+        sp.M0[j] = 0.02f + 8e-6f * fabsf(sp.C[j]);
+        sp.M1[j] = 8e-6f * fabsf(sp.R[j]);
+        sp.lower[j] = use ? (a[j] > 0.0f ? 1.0f : -1.0f) : 0.0f;
+    }
+    return sp;
+}
+
+__device__ __forceinline__ bool row_span(const SpanSetup& sp, float ax, float t, int x_lo, int x_hi,
+                                         int& xs, int& xe) {
+    float lo = -3.0e38f, hi = 3.0e38f;
+    const float at = fabsf(t);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float root = fmaf(sp.R[j], t, sp.C[j]);
+        const float margin = fmaf(sp.M1[j], at, sp.M0[j]);
+        lo = fmaxf(lo, sp.lower[j] > 0.0f ? root - margin : -3.0e38f);
+        hi = fminf(hi, sp.lower[j] < 0.0f ? root + margin : 3.0e38f);
+    }
+    // float -> int conversions saturate, so far-away bounds clip correctly
+    xs = max(x_lo, __float2int_ru(ax + lo));
+    xe = min(x_hi, __float2int_rd(ax + hi));
+    return xs <= xe;
+}
+
 template <int MODE, bool EXACT_DIV>
 __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
-    const bool mine = lane < nb;
-    const int f = mine ? S.qface[lane] : 0;
+    const bool queued = lane < nb;
+    const int f = queued ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
     int ncand = 0;
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1, bh = 1;
-    if (mine) {
+    if (queued) {
         const short4 fb = __ldg(P.face_box + bf);
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
         const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
@@ -517,9 +599,35 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
         bw = min((int)fb.z, tx1) - cx0 + 1;
         bh = min((int)fb.w, ty1) - cy0 + 1;
-        ncand = bw * bh;
     }
     __syncwarp();                                       // queue entries consumed
+    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+
+    // candidate rows: conservative per-row spans (bounding-box rows when the face is degenerate or NaN)
+    unsigned rowmask = 0u;
+    if (queued) {
+        // spans pay off on larger boxes only; degenerate / NaN faces keep their bounding-box rows
+        const bool tight = (bw * bh >= 8) && (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
+        const SpanSetup sps = span_setup(es);
+#pragma unroll 1
+        for (int r = 0; r < bh; ++r) {
+            int xs = cx0, xe = cx0 + bw - 1;
+            bool ok = true;
+            if (tight) ok = row_span(sps, es.ax, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe);
+            if (ok) {
+                const int rr = cy0 - ty0 + r;
+                rowmask |= 1u << rr;
+                ncand += xe - xs + 1;
+                S.span[lane][rr] = (unsigned char)(((xs - tx0) << 4) | (xe - tx0));
+            }
+        }
+    }
+    const unsigned nz = __ballot_sync(FULL, ncand > 0);
+    if (lane == 0) st.visits++;
+    if (nz == 0u) return;
+    const bool mine = ncand > 0;
+    const int nslots = __popc(nz);
+    const int rank = __popc(nz & lanemask_lt());
 
     int incl = ncand;
 #pragma unroll
@@ -528,13 +636,12 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         if (lane >= d) incl += v;
     }
     const int T = __shfl_sync(FULL, incl, 31);
-    if (lane == 0) st.visits++;
 
     float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
-    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
     if (mine) {
-        float4* sl = S.slot + lane * SLOT_VEC;
-        const int box = (cx0 - tx0) | ((cy0 - ty0) << 4) | (bw << 8) | (bh << 13);
+        float4* sl = S.slot + rank * SLOT_VEC;
+        // box word: queue lane (5 bits) | row mask (16 bits) << 5 | (ncand - 1) << 21   (ncand <= 256)
+        const int box = lane | (int)(rowmask << 5) | ((ncand - 1) << 21);
         sl[0] = make_float4(es.ax, es.ay, es.m, es.p);
         sl[1] = make_float4(es.n, es.q, es.k3, __int_as_float(box));
         const double d = (double)es.k3 + 1e-15;                        // diff_fp_for.cu:144 denominator
@@ -552,11 +659,9 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             cB = -__fmul_rn(sgn, mu_out);                             // :190
             sl[3] = make_float4(r0, r1, r2, cA);
         } else {
-            S.mom[0][lane] = 0.0f; S.mom[1][lane] = 0.0f; S.mom[2][lane] = 0.0f;
+            S.mom[0][rank] = 0.0f; S.mom[1][rank] = 0.0f; S.mom[2][rank] = 0.0f;
         }
-        const float ak3 = fabsf(es.k3);
-        const float rd = ((ak3 > 1e-6f) & (ak3 < 1e10f)) ? __frcp_rn(es.k3) : 0.0f;
-        sl[4] = make_float4(cB, __int_as_float(incl - ncand), rd, __int_as_float(f));
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), 0.0f, __int_as_float(f));
     }
     // forward: snapshot of the 8 pixels this lane checks afterwards (4*lane.. and 128+4*lane..)
     float4 old0 = make_float4(0, 0, 0, 0), old1 = old0;
@@ -576,44 +681,51 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
 #pragma unroll
         for (int step = 16; step >= 1; step >>= 1) {
             const int c = i + step;
-            if (c < nb && __float_as_int(S.slot[c * SLOT_VEC + 4].y) <= j0) i = c;
+            if (c < nslots && __float_as_int(S.slot[c * SLOT_VEC + 4].y) <= j0) i = c;
         }
     }
-    int lx = 0, ly = 0, e = 0;
+    // position inside the face: row r, column offset lx within the row's span
+    int e = j0 - __float_as_int(S.slot[i * SLOT_VEC + 4].y);
+    int box = __float_as_int(S.slot[i * SLOT_VEC + 1].w);
+    int n_i = (box >> 21) + 1, ql = box & 31;
+    unsigned rows = ((unsigned)box >> 5) & 0xffffu;
+    int r = __ffs(rows) - 1, rx0 = 0, rlen = 1, lx = 0;
     {
-        const float4 v1 = S.slot[i * SLOT_VEC + 1];
-        const int box = __float_as_int(v1.w);
-        const int w = (box >> 8) & 31;
-        e = j0 - __float_as_int(S.slot[i * SLOT_VEC + 4].y);
-        ly = (int)__fdividef((float)e + 0.5f, (float)w);
-        lx = e - ly * w;
+        int left = e;
+        while (true) {
+            const unsigned sp = S.span[ql][r];
+            rx0 = sp >> 4; rlen = (int)(sp & 15u) - rx0 + 1;
+            if (left < rlen || (rows & (rows - 1u)) == 0u) break;
+            left -= rlen; rows &= rows - 1u; r = __ffs(rows) - 1;
+        }
+        lx = min(left, rlen - 1);
     }
     float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
     bool whole = (e == 0);                               // current face entered at its first candidate
 
+#pragma unroll 1
     for (int t = 0; t < iters; ++t) {
         const bool act = t < mycount;
         const float4* sl = S.slot + i * SLOT_VEC;
-        const float4 v0 = sl[0], v1 = sl[1], v4 = sl[4];
-        const int box = __float_as_int(v1.w);
-        const int w = (box >> 8) & 31, n_i = w * ((box >> 13) & 31);
-        const int px = (box & 15) + lx, py = ((box >> 4) & 15) + ly;
+        const float4 v0 = sl[0], v1 = sl[1];
+        const int px = rx0 + lx, py = r;
         const int pl = (py * TILE + px) & (TILE_PIX - 1);
         bool in = false;
         float k1 = 0.0f, k2 = 0.0f, w0, w1, w2;
         if (act) {
-            in = cover_slot<EXACT_DIV>(v0, v1, v4.z, reinterpret_cast<const double2*>(sl)[2],
+            in = cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
                                        (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
             st.cand++;
         }
         if (IS_FWD) {
             if (in) {
                 const float4 v3 = sl[3];
+                const float cB = sl[4].x;
                 const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));  // :182
                 if (!(bary > 0.0f)) st.nonpos++;                      // :183 assert -> counter
                 st.frag++;
                 atomicOr(&S.f.hitm[pl], 1u << i);
-                S.acc[pl] = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, S.acc[pl]));             // :187,190
+                S.acc[pl] = __fmaf_rn(bary, cB, __fmaf_rn(bary, v3.w, S.acc[pl]));               // :187,190
             }
         } else {
             if (in) {
@@ -621,22 +733,32 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
                 if (g != 0.0f) { st.frag++; M0 += g; A1 = fmaf(g, k1, A1); A2 = fmaf(g, k2, A2); }
             }
         }
-        if (act) {                                       // advance inside the face, or move to the next one
+        if (act) {                                       // next column, next non-empty row, or next face
             ++e; ++lx;
-            if (lx == w) { lx = 0; ++ly; }
-            if (e == n_i) {
-                if (!IS_FWD) {
-                    if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
-                        if (whole) {           // entered at its first candidate and finished here: sole contributor
-                            S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
-                        } else {
-                            shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
+            if (lx == rlen) {
+                lx = 0;
+                if (e == n_i) {
+                    if (!IS_FWD) {
+                        if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
+                            if (whole) {       // entered at its first candidate and finished here: sole contributor
+                                S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
+                            } else {
+                                shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
+                            }
                         }
+                        M0 = 0.0f; A1 = 0.0f; A2 = 0.0f;
+                        whole = true;
                     }
-                    M0 = 0.0f; A1 = 0.0f; A2 = 0.0f;
-                    whole = true;
+                    i = min(i + 1, nslots - 1); e = 0;
+                    box = __float_as_int(S.slot[i * SLOT_VEC + 1].w);
+                    n_i = (box >> 21) + 1; ql = box & 31;
+                    rows = ((unsigned)box >> 5) & 0xffffu;
+                } else {
+                    rows &= rows - 1u;
                 }
-                i = min(i + 1, nb - 1); e = 0; lx = 0; ly = 0;
+                r = __ffs(rows) - 1;
+                const unsigned sp = S.span[ql][r & 15];
+                rx0 = sp >> 4; rlen = (int)(sp & 15u) - rx0 + 1;
             }
         }
     }
@@ -676,26 +798,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             for (int k = 0; k < 8; ++k)
                 if (mymask[k]) S.f.hitm[(k < 4 ? 0 : 128) + 4 * lane + (k & 3)] = mymask[k];
             __syncwarp();
-            for (int base = 0; base < ncp; base += 32) {
-                const bool have = base + lane < ncp;
-                const int pix = have ? (int)S.f.cpix[base + lane] : 0;
-                const int px = pix & 15, py = pix >> 4;
-                float acc = S.acc[pix];
-                unsigned fm = have ? S.f.hitm[pix] : 0u;
-                while (fm) {                                          // ascending face id (diff_fp_for.cu:83)
-                    const int fi = __ffs(fm) - 1;
-                    fm &= fm - 1u;
-                    const float4* sl = S.slot + fi * SLOT_VEC;
-                    const float4 v0 = sl[0], v1 = sl[1], v3 = sl[3], v4 = sl[4];
-                    float k1, k2, w0, w1, w2;
-                    // the face is known to cover the pixel: only the weights are needed again
-                    cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
-                                          (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
-                    const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));
-                    acc = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, acc));
-                }
-                if (have) { S.acc[pix] = acc; S.f.hitm[pix] = 0u; }
-            }
+            redo_conflicted<EXACT_DIV>(S, ncp, tx0, ty0, lane);
         }
         __syncwarp();
         return;
@@ -703,7 +806,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
 
     if (mine) {
         // per-face gradients from the moments of this tile's fragments (face_grads_from_moments)
-        const float m0 = S.mom[0][lane], a1 = S.mom[1][lane], a2 = S.mom[2][lane];
+        const float m0 = S.mom[0][rank], a1 = S.mom[1][rank], a2 = S.mom[2][rank];
         if (m0 != 0.0f || a1 != 0.0f || a2 != 0.0f) {
             const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
             const float cgeo = sgn * (mu_in - mu_out);                // raw mu, no label-0 flip (back.cu:115)
@@ -937,15 +1040,22 @@ k_raster(const RasterParams P) {
             __syncwarp();
 
             // walk the region's chunk list, 32 boxes per ballot, in face order; queue the faces whose
-            // own box overlaps the tile and drain the queue 32 faces at a time
-            int qn = 0;
-            for (int lb = 0; lb < nlist; lb += 32) {
-                const int e = lb + lane;
-                bool hit = false;
-                int cid = 0;
-                if (e < nlist) { cid = C.list_id[e]; hit = box_overlap(__ldg(boxes + cid), tx0, ty0, tx1, ty1); }
-                unsigned m = __ballot_sync(FULL, hit);
-                while (m) {
+            // own box overlaps the tile and drain the queue 32 faces at a time (single call site: the
+            // batch routine is large and must not be inlined twice — it would overflow the I-cache)
+            int qn = 0, lb = 0, cid = 0;
+            unsigned m = 0u;
+            bool exhausted = false;
+            while (true) {
+                while (qn < 32 && !exhausted) {
+                    if (m == 0u) {
+                        if (lb >= nlist) { exhausted = true; break; }
+                        const int e = lb + lane;
+                        bool hit = false;
+                        if (e < nlist) { cid = C.list_id[e]; hit = box_overlap(__ldg(boxes + cid), tx0, ty0, tx1, ty1); }
+                        m = __ballot_sync(FULL, hit);
+                        lb += 32;
+                        continue;
+                    }
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
                     const int f = __shfl_sync(FULL, cid, src) * CHUNK + lane;
@@ -954,28 +1064,21 @@ k_raster(const RasterParams P) {
                     const bool fh = box_overlap(fb, tx0, ty0, tx1, ty1);
                     const unsigned hm = __ballot_sync(FULL, fh);
                     if (lane == 0) st.hits += (hm != 0u);
-                    if (fh) {
-                        const int q = qn + __popc(hm & lanemask_lt());
-                        S.qface[q] = f;
-                    }
+                    if (fh) S.qface[qn + __popc(hm & lanemask_lt())] = f;
                     qn += __popc(hm);
                     __syncwarp();
-                    if (qn >= 32) {
-                        if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
-                        else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, 32, tx0, ty0, tx1, ty1, lane, st);
-                        const int rest = qn - 32;              // < 32: shift the tail to the front
-                        int tf = 0;
-                        if (lane < rest) tf = S.qface[32 + lane];
-                        __syncwarp();
-                        if (lane < rest) S.qface[lane] = tf;
-                        qn = rest;
-                        __syncwarp();
-                    }
                 }
-            }
-            if (qn > 0) {
-                if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
-                else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, qn, tx0, ty0, tx1, ty1, lane, st);
+                if (qn == 0) break;
+                const int nbatch = min(qn, 32);
+                if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                const int rest = qn - nbatch;                  // < 32: shift the tail to the front
+                int tf = 0;
+                if (lane < rest) tf = S.qface[32 + lane];
+                __syncwarp();
+                if (lane < rest) S.qface[lane] = tf;
+                qn = rest;
+                __syncwarp();
             }
 
             // tile epilogue

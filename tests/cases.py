@@ -6,7 +6,7 @@ import numpy as np
 from shapefromprojections_b200.utils import meshgen, util_sino
 
 
-def soup_case(seed=0, B=3, F=1500, H=96, W=96, n_mus=3, reference_safe=False):
+def soup_case(seed=0, B=3, F=1500, H=96, W=96, n_mus=3, reference_safe=False, max_size=30.0):
     """Random triangle soup straight at the Rasterizer boundary (p6/len3/ff/labels/mus).
 
     Mixes tiny and large faces, faces partly off the detector (whole-face reject,
@@ -16,7 +16,7 @@ def soup_case(seed=0, B=3, F=1500, H=96, W=96, n_mus=3, reference_safe=False):
     """
     rng = np.random.default_rng(seed)
     centre = rng.uniform(-6, [W + 6, H + 6], size=(B, F, 1, 2))
-    size = np.exp(rng.uniform(np.log(0.3), np.log(30.0), size=(B, F, 1, 1)))
+    size = np.exp(rng.uniform(np.log(0.3), np.log(max_size), size=(B, F, 1, 1)))
     p = centre + rng.normal(size=(B, F, 3, 2)) * size
     snap = rng.random((B, F)) < 0.25                       # integer coordinates: knife-edge pixels
     p[snap] = np.round(p[snap])
