@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-optimise", action="store_true")
+    ap.add_argument("--optimise-iters", type=int, default=100)
     return ap.parse_args()
 
 
@@ -332,6 +334,8 @@ def main():
                 "achieved": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9, "unit": "GB/s",
                 "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ncu_cfg3_summary.md)"}
+    if not args.no_optimise and world == 1:
+        line["optimise_iteration"] = optimise_iteration(torch, args.optimise_iters)
     if not args.no_cpu_baseline and world == 1:
         gpix, dt, sample = cpu_reference_sample(wl)
         line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": os.cpu_count(), "kind": "port",
@@ -342,6 +346,48 @@ def main():
 
 
 LAUNCHES_PER_STEP = 5   # per angle window: vertex stage, chunk+face boxes, raster forward, raster residual/backward, vertex backward
+
+
+def optimise_iteration(torch, niter):
+    """BASELINE.json's second metric, 's per optimise iteration', on config 2: 2bunnyA geometry
+    (30 x 192 x 192), icosphere(4) initial mesh (V=2562, F=5120), synthetic star-shaped target with
+    eta = 0.3 noise, the reference's default weights (parse_args.py:13-23).  Times ctdr.optimize.run
+    (fused data term + sparse regularisers + Adam), one host sync per iteration like the reference."""
+    import tempfile
+    import types
+    from shapefromprojections_b200 import optimize, workloads
+    from shapefromprojections_b200.dataset.dataset import SinoDataset
+    from shapefromprojections_b200.function import rasterizer as R
+    from shapefromprojections_b200.model.vanilla import Model
+    wl = workloads.make_workload("cfg1")                      # same geometry numbers as data/2bunnyA
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gd = R.GeometryDevice(wl["geom"], dev)
+    gt_v, gt_f = workloads.star_surface(4)
+    labels = torch.as_tensor(np.tile(np.array([1, 0], np.int32), (gt_f.shape[0], 1))).to(dev)
+    clean, _, _ = R.project_forward(gd, torch.as_tensor(gt_v).to(dev), torch.as_tensor(gt_f).to(torch.int32).to(dev),
+                                    labels, torch.tensor([0.0, 1.0], device=dev), torch.arange(wl["nangles"], device=dev))
+    ds = SinoDataset.from_arrays(wl["geom"], clean.cpu().numpy(), nmaterials=2, eta=0.3)
+    labels_v = np.ones(wl["verts"].shape[0], dtype=np.int32)
+    model = Model((wl["verts"], wl["faces"], labels_v, wl["labels"]), wl["geom"], 2, [0.0, 1.0], 1,
+                  wlap=10.0, wflat=0.01).to(dev)
+    model.set_mu0(ds.p.to(dev))
+    with tempfile.TemporaryDirectory() as tmp:
+        args = types.SimpleNamespace(data="2bunnyA", lr=0.01, b=0, wedge=2.0, wlap=10.0, wflat=0.01, verbose=0,
+                                     dresult=tmp + "/")
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            optimize.run(model, ds, 10, args, fused=True, log_every=10 ** 9)          # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            optimize.run(model, ds, 10 + niter, args, epoch_start=10, fused=True, log_every=10 ** 9)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        log = open(tmp + "/log.txt").read().splitlines()
+    l2 = [float(l.split("l2_loss:")[1].split()[0]) for l in log if l.startswith("~ ") and "l2_loss" in l]
+    return {"workload": "cfg2: 2bunnyA geometry 30x192x192, icosphere(4) V=2562 F=5120, star-shaped target + eta=0.3 noise, "
+                        "wlap=10 wedge=2 wflat=0.01 lr=0.01 (parse_args.py defaults)",
+            "s_per_iteration": dt / niter, "iterations": niter, "l2_first": l2[0] if l2 else None,
+            "l2_last": l2[-1] if l2 else None, "mus": [float(x) for x in model.mus.detach().cpu()]}
 
 
 def wl_pin(torch, arr):

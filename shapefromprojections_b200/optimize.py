@@ -101,16 +101,17 @@ def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_ev
                 loss.backward()
             opt.step()
             model.mus.data.clamp_(min=0.0)
-        loss_now = float(loss)                        # the one host sync of the iteration
+        loss_now = float(loss.detach())               # the one host sync of the iteration
         elapsed = time.time() - start
         if loss_prev is not None and args.b == 0 and 0 < loss_prev - loss_now < 1e-11:
             print("! converged")
             break
         loss_prev = loss_now
-        ledge = float(edge_loss) if args.wedge > 0. else ledge
-        llap = float(lap_loss) if args.wlap > 0. else llap
-        lflat = float(flat_loss) if args.wflat > 0. else lflat
-        log += (f"~ {epoch:03d} l2_loss: {float(data_loss):.8f} edge: {ledge:.6f} lap: {llap:.6f} flat: {lflat:.6f} "
+        scalar = lambda v: float(v.detach()) if torch.is_tensor(v) else float(v)
+        ledge = scalar(edge_loss) if args.wedge > 0. else ledge
+        llap = scalar(lap_loss) if args.wlap > 0. else llap
+        lflat = scalar(flat_loss) if args.wflat > 0. else lflat
+        log += (f"~ {epoch:03d} l2_loss: {float(data_loss.detach()):.8f} edge: {ledge:.6f} lap: {llap:.6f} flat: {lflat:.6f} "
                 f"mus: {str(model.mus.cpu().detach().numpy())} time: {elapsed:.4f}\n")
         if epoch % log_every == 0 or epoch == niter - 1:
             if mask_valid is None:

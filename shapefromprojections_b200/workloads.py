@@ -50,3 +50,13 @@ def algorithmic_bytes(B, H, W, V, F, n_gpus=1):
     """8 B per detector pixel (4 B sinogram store + 4 B target/gradient load)
     plus the replicated mesh/geometry term per GPU."""
     return 8 * B * H * W + n_gpus * (24 * V + 20 * F) + 48 * B
+
+
+def star_surface(subdiv=4):
+    """Ground-truth shape of config 2: a star-shaped radial perturbation of the
+    icosphere, r(theta, phi) = 0.45 * (1 + 0.25 * sin(3 theta) * sin(4 phi))."""
+    v, f = meshgen.icosphere(subdiv, 1.0, 0.0)
+    theta = np.arccos(np.clip(v[:, 2], -1.0, 1.0))
+    phi = np.arctan2(v[:, 1], v[:, 0])
+    r = 0.45 * (1.0 + 0.25 * np.sin(3 * theta) * np.sin(4 * phi))
+    return (v * r[:, None] + 1e-4).astype(np.float32), f.astype(np.int64)
