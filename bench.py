@@ -382,11 +382,19 @@ def optimise_iteration(torch, niter):
             optimize.run(model, ds, 10 + niter, args, epoch_start=10, fused=True, log_every=10 ** 9)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            # same iteration captured in a CUDA graph (graph build outside the timed region)
+            git = optimize.GraphedIteration(model, args, torch.arange(wl["nangles"]), ds.p)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(niter):
+                last = git.step().tolist()           # one host sync per iteration, like the reference's loss.item()
+            dt_graph = time.perf_counter() - t0
         log = open(tmp + "/log.txt").read().splitlines()
     l2 = [float(l.split("l2_loss:")[1].split()[0]) for l in log if l.startswith("~ ") and "l2_loss" in l]
     return {"workload": "cfg2: 2bunnyA geometry 30x192x192, icosphere(4) V=2562 F=5120, star-shaped target + eta=0.3 noise, "
                         "wlap=10 wedge=2 wflat=0.01 lr=0.01 (parse_args.py defaults)",
-            "s_per_iteration": dt / niter, "iterations": niter, "l2_first": l2[0] if l2 else None,
+            "s_per_iteration": dt / niter, "s_per_iteration_cuda_graph": dt_graph / niter, "l2_after_graphed": last[0],
+            "iterations": niter, "l2_first": l2[0] if l2 else None,
             "l2_last": l2[-1] if l2 else None, "mus": [float(x) for x in model.mus.detach().cpu()]}
 
 

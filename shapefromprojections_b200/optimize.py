@@ -52,7 +52,64 @@ def projection_step(model, idx_angles, p_batch, exchange=None):
     return loss.to(torch.float32), phat, exchange.scalars[1]
 
 
-def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_every=60):
+class GraphedIteration:
+    """One full-batch optimiser iteration captured in a CUDA graph.
+
+    The iteration of ``run`` — fused data term, sparse regularisers and their autograd, Adam step,
+    ``mus.clamp_(min=0)`` — is launch-bound at the reference's own problem sizes (config 1/2: tens of
+    microseconds of kernels behind ~100 launches).  Capturing it once and replaying removes the
+    Python/launch overhead; nothing in the iteration synchronises with the host.  ``step()`` replays
+    and returns the device tensor ``[data_loss, edge, lap, flat]`` of the iteration.
+    """
+
+    def __init__(self, model, args, idx_angles, p_full, lr=None):
+        self.model, self.args = model, args
+        dev = model.vertices.device
+        self.idx = torch.as_tensor(idx_angles).to(device=dev, dtype=torch.int64)
+        self.p = p_full.to(dev).contiguous()
+        self.exchange = distributed.GradientExchange(model.vertices.shape[0], model.mus.numel(), dev)
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.lr = torch.tensor(float(args.lr if lr is None else lr), device=dev)
+        self.opt = torch.optim.Adam(params, lr=self.lr, betas=(0.9, 0.99), capturable=True)
+        self.stats = torch.zeros(4, device=dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up on a side stream (allocator, Adam state)
+                self._iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self.phat = self._phat
+
+    def _iteration(self):
+        model, args = self.model, self.args
+        self.opt.zero_grad(set_to_none=True)
+        data_loss, self._phat, _ = projection_step(model, self.idx, self.p, self.exchange)
+        vertices = model.get_displaced_vertices()
+        zero = torch.zeros((), device=vertices.device)
+        edge = R_edge(model, vertices) if args.wedge > 0. else zero
+        lap = model.laplacian_loss(vertices).mean() if model.use_lap_loss else zero
+        flat = model.flat_loss(vertices) if model.use_flat_loss else zero
+        reg = args.wedge * edge + args.wlap * lap + args.wflat * flat
+        if reg.requires_grad:
+            reg.backward()
+        self.opt.step()
+        model.mus.data.clamp_(min=0.0)
+        self.stats.copy_(torch.stack([data_loss.detach(), edge.detach(), lap.detach(), flat.detach()]))
+
+    def set_lr(self, lr):
+        self.lr.fill_(float(lr))
+
+    def step(self):
+        self.graph.replay()
+        return self.stats
+
+
+def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_every=60, graphed=False):
     if fused is None:
         fused = getattr(model.fp, "fused", False)
     print("@ model.mus", model.mus)
@@ -68,6 +125,10 @@ def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_ev
         ds_loader = torch.utils.data.DataLoader(ds, batch_size=args.b, shuffle=True, num_workers=0,
                                                 drop_last=True, pin_memory=True)
     exchange = distributed.GradientExchange(model.vertices.shape[0], model.mus.numel(), dev) if fused else None
+    graph_it = None
+    if graphed and fused and use_adam and args.b == 0:
+        graph_it = GraphedIteration(model, args, ds_loader[0][0], ds_loader[0][1])
+        opt = graph_it.opt
     ledge = llap = lflat = 0.
     loss_prev = None
     phat = mask_valid = None
@@ -79,7 +140,13 @@ def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_ev
             print("@ args.lr", args.lr)
         torch.cuda.synchronize(dev)
         start = time.time()
-        for idx_angles, p_batch in ds_loader:
+        if graph_it is not None:
+            graph_it.set_lr(args.lr)
+            vals = graph_it.step().tolist()              # the one host sync of the iteration
+            data_loss, edge_loss, lap_loss, flat_loss = (torch.tensor(v) for v in vals)
+            loss = data_loss + args.wedge * edge_loss + args.wlap * lap_loss + args.wflat * flat_loss
+            phat, mask_valid = graph_it.phat, None
+        for idx_angles, p_batch in (ds_loader if graph_it is None else []):
             if args.b > 0:
                 p_batch = p_batch.to(dev, non_blocking=True)
             opt.zero_grad()

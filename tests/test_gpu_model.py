@@ -102,3 +102,25 @@ def test_reference_rasterizer_module_runs_on_new_kernels(cuda_lib):
     od = oracle.rasterizer_backward(g, o, c["p6"], c["len3"], c["ff"], c["labels"], c["mus"])
     for a, b in zip((dp, dl, dm), od):
         assert np.linalg.norm(a.cpu().numpy() - b) <= 2e-4 * np.linalg.norm(b)
+
+
+def test_cuda_graph_iteration_follows_the_eager_trajectory(cuda_lib, tmp_path):
+    """GraphedIteration (whole optimiser iteration replayed from a CUDA graph) == optimize.run eagerly."""
+    from ctdr import optimize
+    from ctdr.dataset.dataset import SinoDataset
+    geom = cases.parallel_geometry(12, 96, 2.0 / 96)
+    p = target_sinogram(geom)
+    ds = SinoDataset.from_arrays(geom, p.cpu().numpy(), nmaterials=2, eta=0.0)
+    args = types.SimpleNamespace(data="2starA", lr=0.01, b=0, wedge=1.0, wlap=10.0, wflat=0.01, verbose=0,
+                                 dresult=str(tmp_path) + "/")
+    a = make_model(geom, wlap=10.0, wflat=0.01); a.set_mu0(ds.p.cuda())
+    optimize.run(a, ds, 25, args, fused=True, log_every=10 ** 9)
+    eager = [float(l.split("l2_loss:")[1].split()[0]) for l in open(tmp_path / "log.txt").read().splitlines() if l.startswith("~ 0")]
+    b = make_model(geom, wlap=10.0, wflat=0.01); b.set_mu0(ds.p.cuda())
+    # the graph constructor runs 3 warm-up iterations on the model (the capture pass itself executes nothing)
+    git = optimize.GraphedIteration(b, args, torch.arange(12), ds.p)
+    graphed = [git.step().tolist()[0] for _ in range(21)]
+    # replay k of the graphed run (0-based) is eager iteration k + 3
+    for k in (0, 5, 20):
+        assert abs(graphed[k] - eager[k + 3]) <= 2e-3 * eager[k + 3] + 1e-7, (k, graphed[k], eager[k + 3])
+    assert graphed[-1] < eager[0] / 3
