@@ -345,7 +345,7 @@ def main():
         dist.destroy_process_group()
 
 
-LAUNCHES_PER_STEP = 5   # per angle window: vertex stage, chunk+face boxes, raster forward, raster residual/backward, vertex backward
+LAUNCHES_PER_STEP = 7   # per angle window: vertex transform, face assemble, chunk+face boxes, super-region lists, raster forward, raster residual/backward, vertex backward
 
 
 def optimise_iteration(torch, niter):

@@ -301,25 +301,27 @@ int check_geom(int kind) {
 
 struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
+    float4* vt;          // [window, V] per-vertex transform records
     RasterWs rws;
     int window;   // angles per window
 };
 
-size_t project_per_angle_bytes(int F, bool bwd) {
+size_t project_per_angle_bytes(int V, int F, bool bwd) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+    return (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
            MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
-int project_ws_layout(int B, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 14 * 256;
-    const size_t per = project_per_angle_bytes(F, bwd);
+int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
+    const size_t slack = 16 * 256;
+    const size_t per = project_per_angle_bytes(V, F, bwd);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
     if (win > B) win = B;
     ws->window = (int)win;
     char* p = static_cast<char*>(base);
     size_t off = 0;
+    ws->vt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
     ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
     ws->len3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
     ws->ff = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 4, 256);
@@ -338,6 +340,16 @@ int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* 
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
     k_vertex_forward<<<(unsigned)blocks, 256, 0, st>>>(P, p6, len3, ff);
     CTDR_CUDA(cudaGetLastError(), "k_vertex_forward launch");
+    return 0;
+}
+
+int launch_vertex_forward_staged(const VertexParams& P, float4* vt, float* p6, float* len3, float* ff, cudaStream_t st) {
+    const long long nv = (long long)P.B * P.V, nf = (long long)P.B * P.F;
+    if ((nv + 255) / 256 > 0x7fffffffLL || (nf + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    k_vertex_transform<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(P, vt);
+    CTDR_CUDA(cudaGetLastError(), "k_vertex_transform launch");
+    k_face_assemble<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(P, vt, p6, len3, ff);
+    CTDR_CUDA(cudaGetLastError(), "k_face_assemble launch");
     return 0;
 }
 
@@ -460,14 +472,14 @@ int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles, const in
 }
 
 size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_backward) {
-    (void)V; (void)H; (void)W;
-    if (B <= 0 || F <= 0) return 0;
-    const size_t per = project_per_angle_bytes(F, need_backward != 0);
+    (void)H; (void)W;
+    if (B <= 0 || F <= 0 || V <= 0) return 0;
+    const size_t per = project_per_angle_bytes(V, F, need_backward != 0);
     const size_t budget = (size_t)6 << 30;               // default window budget: 6 GiB
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 14 * 256;
+    return per * (size_t)win + 16 * 256;
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -482,12 +494,12 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !im || !workspace) return fail(CTDR_E_NULL, "ctdr_project_forward: null pointer");
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, F, H, W, false, workspace, workspace_bytes, &ws)) return rc;
+    if (int rc = project_ws_layout(B, V, F, H, W, false, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im + (size_t)b0 * hw;
         P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
@@ -507,12 +519,12 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
                                  void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                                  cudaStream_t stream) {
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
         CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
@@ -567,12 +579,12 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
     // per angle window: vertex stage once, forward raster (phat is an output the caller keeps), then the
     // residual/backward sweep over the same staged p6/len3/ff and face boxes
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward(VP, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;

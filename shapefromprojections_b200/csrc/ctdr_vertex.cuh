@@ -150,47 +150,105 @@ k_vertex_forward(const VertexParams P, float* __restrict__ p6, float* __restrict
     ff[gid] = facing;
 }
 
+// Two-stage variant used by the fused projector: every vertex is transformed once per angle
+// (thread per (angle, vertex) -> float4 {px, py, len, camera x}) and the faces gather three records
+// each, instead of transforming each vertex once per incident face (~6x).  Same arithmetic, same
+// results as k_vertex_forward.
+__global__ void __launch_bounds__(256)
+k_vertex_transform(const VertexParams P, float4* __restrict__ vt) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.B * P.V) return;
+    const int b = (int)(gid / P.V), v = (int)(gid % P.V);
+    const AngleConst A = angle_const(P, b);
+    const VertexOut o = project_vertex(P, A, __ldg(P.verts + 3 * v), __ldg(P.verts + 3 * v + 1), __ldg(P.verts + 3 * v + 2));
+    vt[gid] = make_float4(o.px, o.py, o.len, o.cx);
+}
+
+__global__ void __launch_bounds__(256)
+k_face_assemble(const VertexParams P, const float4* __restrict__ vt, float* __restrict__ p6,
+                float* __restrict__ len3, float* __restrict__ ff) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P.B * P.F) return;
+    const int b = (int)(gid / P.F), f = (int)(gid % P.F);
+    const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
+    const float4* row = vt + (long long)b * P.V;
+    const float4 a = __ldg(row + i0), bb = __ldg(row + i1), c = __ldg(row + i2);
+    float facing;
+    if (P.kind == 0) {
+        // camera-space normal z from (camera x, camera y = -z_world) (fp_opengl.py:137-148)
+        const float ya = -__ldg(P.verts + 3 * i0 + 2), yb = -__ldg(P.verts + 3 * i1 + 2), yc = -__ldg(P.verts + 3 * i2 + 2);
+        const float e1x = __fsub_rn(bb.w, a.w), e1y = __fsub_rn(yb, ya);
+        const float e2x = __fsub_rn(c.w, a.w), e2y = __fsub_rn(yc, ya);
+        facing = -__fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    } else {
+        const float x0 = __ldg(P.verts + 3 * i0), y0 = __ldg(P.verts + 3 * i0 + 1), z0 = __ldg(P.verts + 3 * i0 + 2);
+        const float x1 = __ldg(P.verts + 3 * i1), y1 = __ldg(P.verts + 3 * i1 + 1), z1 = __ldg(P.verts + 3 * i1 + 2);
+        const float x2 = __ldg(P.verts + 3 * i2), y2 = __ldg(P.verts + 3 * i2 + 1), z2 = __ldg(P.verts + 3 * i2 + 2);
+        const float e1x = __fsub_rn(x1, x0), e1y = __fsub_rn(y1, y0), e1z = __fsub_rn(z1, z0);
+        const float e2x = __fsub_rn(x2, x0), e2y = __fsub_rn(y2, y0), e2z = __fsub_rn(z2, z0);
+        const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+        const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+        const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+        const AngleConst A = angle_const(P, b);
+        float rx = A.Sx, ry = A.Sy, rz = A.Sz;
+        if (P.kind == 2) {      // unit ray to the face's first vertex, as project_vertex forms it (fp_vecs.py:141-145)
+            const float Rx = __fsub_rn(x0, A.Sx), Ry = __fsub_rn(y0, A.Sy), Rz = __fsub_rn(z0, A.Sz);
+            rx = __fdiv_rn(Rx, a.z); ry = __fdiv_rn(Ry, a.z); rz = __fdiv_rn(Rz, a.z);
+        }
+        facing = __fadd_rn(__fadd_rn(__fmul_rn(rx, nx), __fmul_rn(ry, ny)), __fmul_rn(rz, nz));
+    }
+    float2* o = reinterpret_cast<float2*>(p6 + gid * 6);
+    o[0] = make_float2(a.x, a.y); o[1] = make_float2(bb.x, bb.y); o[2] = make_float2(c.x, c.y);
+    len3[gid * 3 + 0] = a.z; len3[gid * 3 + 1] = bb.z; len3[gid * 3 + 2] = c.z;
+    ff[gid] = facing;
+}
+
 // cotangent of one vertex: (gpx, gpy, glen) -> d/d(x,y,z), hand-written reverse mode of
-// project_vertex (== what torch autograd does through fp_opengl.py:87-158 / fp_vecs.py:101-173)
+// project_vertex (== what torch autograd does through fp_opengl.py:87-158 / fp_vecs.py:101-173).
+// Only the intermediates the transposed Jacobian needs are recomputed (no px/py).
 __device__ __forceinline__ void vertex_vjp(const VertexParams& P, const AngleConst& A,
                                            float x, float y, float z, float gpx, float gpy, float glen,
                                            float& gx, float& gy, float& gz) {
-    const VertexOut o = project_vertex(P, A, x, y, z);
     if (P.kind == 0) {
-        const float il = 1.0f / o.len;
-        const float gxr = gpx * (0.5f * (float)P.W * P.P00) + glen * o.cx * il;
-        const float gcy = gpy * (-0.5f * (float)P.H * P.P11) + glen * o.cy * il;   // cam y = -z
-        const float gyr = glen * o.cz * il;
+        const float xr = x * A.ct + y * A.st, yr = -x * A.st + y * A.ct;
+        const float cz = yr - P.msv;
+        const float il = rsqrtf(xr * xr + z * z + cz * cz);
+        const float gxr = gpx * (0.5f * (float)P.W * P.P00) + glen * xr * il;
+        const float gyr = glen * cz * il;
         gx = gxr * A.ct - gyr * A.st;
         gy = gxr * A.st + gyr * A.ct;
-        gz = -gcy;
+        gz = gpy * (0.5f * (float)P.H * P.P11) + glen * z * il;      // cam y = -z: d(py)/dz = +H*P11/2
         return;
     }
     // P = base + t*r ; px = (P - DetS).{x|y} / u.{x|y} ; py = (P - DetS).z / vz
     float gPx = 0.0f, gPy = 0.0f;
-    if (A.use_x) gPx = gpx / A.ux; else gPy = gpx / A.uy;
-    const float gPz = gpy / A.vz;
+    if (A.use_x) gPx = __fdividef(gpx, A.ux); else gPy = __fdividef(gpx, A.uy);
+    const float gPz = __fdividef(gpy, A.vz);
     if (P.kind == 1) {
         // base = v, r = -S (constant), t = -(N.v + msv)/NR, len = t
-        const float NR = A.N0 * o.cx + A.N1 * o.cy;
-        const float gt = gPx * o.cx + gPy * o.cy + gPz * o.cz + glen;
-        const float gNS = -gt / NR;
+        const float rx = -A.Sx, ry = -A.Sy, rz = -A.Sz;
+        const float NR = A.N0 * rx + A.N1 * ry;
+        const float gt = gPx * rx + gPy * ry + gPz * rz + glen;
+        const float gNS = -__fdividef(gt, NR);
         gx = gPx + gNS * A.N0;
         gy = gPy + gNS * A.N1;
         gz = gPz;
         return;
     }
     // cone: R = v - S, len = |R|, r = R/len, t = coeff/(N.r_xy + 1e-10), P = S + t*r
-    const float NRe = A.N0 * o.cx + A.N1 * o.cy + 1e-10f;
-    const float gt = gPx * o.cx + gPy * o.cy + gPz * o.cz;
-    float grx = o.t * gPx, gry = o.t * gPy, grz = o.t * gPz;
-    const float gNR = -gt * o.t / NRe;
+    const float Rx = x - A.Sx, Ry = y - A.Sy, Rz = z - A.Sz;
+    const float il = rsqrtf(Rx * Rx + Ry * Ry + Rz * Rz);
+    const float rx = Rx * il, ry = Ry * il, rz = Rz * il;
+    const float iNR = __fdividef(1.0f, A.N0 * rx + A.N1 * ry + 1e-10f);
+    const float t = A.coeff * iNR;
+    const float gt = gPx * rx + gPy * ry + gPz * rz;
+    float grx = t * gPx, gry = t * gPy, grz = t * gPz;
+    const float gNR = -gt * t * iNR;
     grx += gNR * A.N0; gry += gNR * A.N1;
-    const float il = 1.0f / o.len;
-    const float rdot = o.cx * grx + o.cy * gry + o.cz * grz;
-    gx = (grx - o.cx * rdot) * il + glen * o.cx;
-    gy = (gry - o.cy * rdot) * il + glen * o.cy;
-    gz = (grz - o.cz * rdot) * il + glen * o.cz;
+    const float rdot = rx * grx + ry * gry + rz * grz;
+    gx = (grx - rx * rdot) * il + glen * rx;
+    gy = (gry - ry * rdot) * il + glen * ry;
+    gz = (grz - rz * rdot) * il + glen * rz;
 }
 
 // thread per face, angle slices along grid.y: sums the cotangents of the face's three corners over
