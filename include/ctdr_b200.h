@@ -175,7 +175,12 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles,
                          void* workspace, size_t workspace_bytes,
                          int64_t* stats, unsigned flags, ctdr_stream_t stream);
 
-/* grad_im [B,H,W], im [B,H,W] (forward output) -> ACCUMULATES grad_verts [V,3], grad_mus [n_mus]. */
+/* grad_im [B,H,W], im [B,H,W] (forward output) -> ACCUMULATES grad_verts [V,3], grad_mus [n_mus].
+ * vadj_start [V+1] / vadj_corner [3F] (int32, may be NULL unless CTDR_FLAG_DETERMINISTIC): for every
+ * vertex the face corners (3*face + corner) that reference it, grouped by vertex in a fixed order
+ * (CSR).  With CTDR_FLAG_DETERMINISTIC the sweep uses single-writer kernels and fixed summation
+ * orders only (face-owner raster backward, adjacency gather for the vertices, tree reductions for
+ * grad_mus and the loss): bit-reproducible results, no atomics. */
 int ctdr_project_backward(int geom_kind, const float* geom, int nangles,
                           const int64_t* idx_angles, int B,
                           const float* verts, int V, const int32_t* faces, int F,
@@ -183,6 +188,7 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles,
                           int H, int W, double spacing_x, double spacing_y, double max_sino_val,
                           const float* grad_im, const float* im,
                           float* grad_verts, float* grad_mus,
+                          const int32_t* vadj_start, const int32_t* vadj_corner,
                           void* workspace, size_t workspace_bytes,
                           int64_t* stats, unsigned flags, ctdr_stream_t stream);
 
@@ -199,6 +205,7 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles,
                                int H, int W, double spacing_x, double spacing_y, double max_sino_val,
                                const float* target, float* phat,
                                float* grad_verts, float* grad_mus, double* out2,
+                               const int32_t* vadj_start, const int32_t* vadj_corner,
                                void* workspace, size_t workspace_bytes,
                                int64_t* stats, unsigned flags, ctdr_stream_t stream);
 

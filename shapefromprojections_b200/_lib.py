@@ -38,9 +38,9 @@ SIGNATURES = {
     "ctdr_project_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
                                   _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_project_backward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
-                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_project_residual_step": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
-                                        _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
 }
 
 _lib = None

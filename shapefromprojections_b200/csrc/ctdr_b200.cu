@@ -55,7 +55,7 @@ int pick_region_tiles(int B, int F, int H, int W) {
     // region lists are long (very fine meshes: fewer list segments).  Measured on config 3 / north star.
     int rt = 8;
     const long long regions8 = (long long)((W + 8 * TILE - 1) / (8 * TILE)) * ((H + 8 * TILE - 1) / (8 * TILE));
-    if (regions8 * B < 64LL * 148 || F > 300000) rt = 4;
+    if (regions8 * B < 128LL * 148 || F > 300000) rt = 4;
     const long long regions4 = (long long)((W + 4 * TILE - 1) / (4 * TILE)) * ((H + 4 * TILE - 1) / (4 * TILE));
     if (regions4 * B < 2LL * 148) rt = 2;
     return rt;
@@ -116,7 +116,7 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
 // row-major order and is the only writer of its 9 gradient values; the per-face attenuation
 // terms go to `fs` and are reduced in a fixed tree by k_mus_reduce.
 // ---------------------------------------------------------------------------------------------
-template <bool PREFILTER>
+template <bool PREFILTER, bool RESID>
 __global__ void __launch_bounds__(128)
 k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,10 +135,18 @@ k_backward_faceowner(const RasterParams P, float* __restrict__ fs) {
     for (int y = iy0; y <= iy1; ++y)
         for (int x = ix0; x <= ix1; ++x) {
             const long long o = base + (long long)y * P.W + x;
-            const float g = __ldg(P.grad_im + o);
-            if (g == 0.0f) continue;
-            const float v = __ldg(P.im_in + o);
-            if (((double)v < -1e-5) || (v > P.msv)) continue;              // diff_fp_for.cu:69-73
+            float g;
+            if (RESID) {        // gradient of sum_valid (target - phat)^2 formed on the fly (fp_vecs.py:10-13 mask)
+                const float v = __ldg(P.im_in + o);
+                if (!(v > -1e-6f && v <= P.mask_hi)) continue;
+                g = 2.0f * (v - __ldg(P.target + o));
+                if (g == 0.0f) continue;
+            } else {
+                g = __ldg(P.grad_im + o);
+                if (g == 0.0f) continue;
+                const float v = __ldg(P.im_in + o);
+                if (((double)v < -1e-5) || (v > P.msv)) continue;          // diff_fp_for.cu:69-73
+            }
             float s, t, k1, k2, w0, w1, w2;
             if (!cover_exact<PREFILTER>(es, (float)x, (float)y, s, t, k1, k2, w0, w1, w2)) continue;
             M0 += g; A1 += g * k1; A2 += g * k2;
@@ -213,6 +221,61 @@ __global__ void k_selftest_quotient(unsigned long long per_thread, unsigned seed
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// deterministic masked-L2 data term: fixed slice per block, fixed shared-memory tree, then one thread
+// adds the block partials in order
+__global__ void __launch_bounds__(256)
+k_residual_partials(const float* __restrict__ phat, const float* __restrict__ target, long long n, float mask_hi,
+                    double* __restrict__ partials) {
+    __shared__ double sl[256], sc[256];
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long i0 = (long long)blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    double loss = 0.0, cnt = 0.0;
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+        const float v = __ldg(phat + i);
+        if (v > -1e-6f && v <= mask_hi) { const double d = (double)(v - __ldg(target + i)); loss += d * d; cnt += 1.0; }
+    }
+    sl[threadIdx.x] = loss; sc[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) { sl[threadIdx.x] += sl[threadIdx.x + d]; sc[threadIdx.x] += sc[threadIdx.x + d]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = sl[0]; partials[2 * blockIdx.x + 1] = sc[0]; }
+}
+
+__global__ void k_residual_final(const double* __restrict__ partials, int nblocks, double* __restrict__ out2) {
+    double loss = 0.0, cnt = 0.0;
+    for (int i = 0; i < nblocks; ++i) { loss += partials[2 * i]; cnt += partials[2 * i + 1]; }
+    out2[0] += loss; out2[1] += cnt;
+}
+
+// deterministic vertex backward: one thread owns one vertex, sums the cotangents of its incident
+// face corners (adjacency in fixed order) angle by angle and is the only writer of its gradient
+__global__ void __launch_bounds__(128)
+k_vertex_backward_gather(const VertexParams P, const int* __restrict__ vstart, const int* __restrict__ vcorner,
+                         const float* __restrict__ gp6, const float* __restrict__ glen3, float* __restrict__ grad_verts) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.V) return;
+    const float x = __ldg(P.verts + 3 * v), y = __ldg(P.verts + 3 * v + 1), z = __ldg(P.verts + 3 * v + 2);
+    const int c0 = __ldg(vstart + v), c1 = __ldg(vstart + v + 1);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    for (int b = 0; b < P.B; ++b) {
+        float gpx = 0.0f, gpy = 0.0f, gl = 0.0f;
+        for (int c = c0; c < c1; ++c) {
+            const int corner = __ldg(vcorner + c);
+            const int f = corner / 3, k = corner - 3 * f;
+            const long long bf = (long long)b * P.F + f;
+            gpx += __ldg(gp6 + bf * 6 + 2 * k); gpy += __ldg(gp6 + bf * 6 + 2 * k + 1); gl += __ldg(glen3 + bf * 3 + k);
+        }
+        if (gpx == 0.0f && gpy == 0.0f && gl == 0.0f) continue;
+        const AngleConst A = angle_const(P, b);
+        float gx, gy, gz;
+        vertex_vjp(P, A, x, y, z, gpx, gpy, gl, gx, gy, gz);
+        ax += gx; ay += gy; az += gz;
+    }
+    grad_verts[3 * v] += ax; grad_verts[3 * v + 1] += ay; grad_verts[3 * v + 2] += az;
+}
+
 struct RasterWs {
     short4* boxes;
     short4* face_boxes;
@@ -262,8 +325,8 @@ int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream
         const long long n = (long long)P.B * P.F;
         const long long blocks = (n + 127) / 128;
         if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
-        if (flags & CTDR_FLAG_NO_PREFILTER) k_backward_faceowner<false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
-        else k_backward_faceowner<true><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        if (flags & CTDR_FLAG_NO_PREFILTER) k_backward_faceowner<false, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        else k_backward_faceowner<true, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
         CTDR_CUDA(cudaGetLastError(), "k_backward_faceowner launch");
         k_mus_reduce<<<P.n_mus, 1024, 0, st>>>(ws.fs, P.labels2, P.B, P.F, P.n_mus, P.grad_mus);
         CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
@@ -302,18 +365,22 @@ int check_geom(int kind) {
 struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
     float4* vt;          // [window, V] per-vertex transform records
+    float* fs;           // [window, F] per-face attenuation terms (deterministic backward)
+    double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
     RasterWs rws;
     int window;   // angles per window
 };
 
+constexpr int DET_LOSS_BLOCKS = 1024;
+
 size_t project_per_angle_bytes(int V, int F, bool bwd) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+    return (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
            MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 16 * 256;
+    const size_t slack = 18 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
     const size_t per = project_per_angle_bytes(V, F, bwd);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -329,6 +396,8 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     if (bwd) {
         ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
         ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
+        ws->fs = reinterpret_cast<float*>(p + off);    off += align_up((size_t)win * F * 4, 256);
+        ws->partials = reinterpret_cast<double*>(p + off); off += align_up(2 * DET_LOSS_BLOCKS * sizeof(double), 256);
     }
     raster_ws_layout((int)win, F, H, W, false, false, &ws->rws, p + off);
     return 0;
@@ -363,6 +432,32 @@ int launch_vertex_backward(const VertexParams& P, const float* gp6, const float*
     dim3 grid((unsigned)face_blocks, (unsigned)((P.B + per - 1) / per));
     k_vertex_backward<<<grid, 256, 0, st>>>(P, gp6, glen3, grad_verts, per);
     CTDR_CUDA(cudaGetLastError(), "k_vertex_backward launch");
+    return 0;
+}
+
+// deterministic residual/backward sweep of one angle window (CTDR_FLAG_DETERMINISTIC): single-writer
+// kernels only, fixed summation orders everywhere
+int deterministic_window(RasterParams P, const VertexParams& VP, const ProjectWs& ws, const int* vstart,
+                         const int* vcorner, float* grad_verts, bool resid, unsigned flags, cudaStream_t st) {
+    const long long n = (long long)P.B * P.F;
+    const long long blocks = (n + 127) / 128;
+    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    const bool exact = (flags & CTDR_FLAG_NO_PREFILTER) != 0;
+    if (resid) {
+        const long long npix = (long long)P.B * P.H * P.W;
+        k_residual_partials<<<DET_LOSS_BLOCKS, 256, 0, st>>>(P.im_in, P.target, npix, P.mask_hi, ws.partials);
+        k_residual_final<<<1, 1, 0, st>>>(ws.partials, DET_LOSS_BLOCKS, P.out2);
+        if (exact) k_backward_faceowner<false, true><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        else k_backward_faceowner<true, true><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+    } else {
+        if (exact) k_backward_faceowner<false, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+        else k_backward_faceowner<true, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
+    }
+    CTDR_CUDA(cudaGetLastError(), "k_backward_faceowner launch");
+    k_mus_reduce<<<P.n_mus, 1024, 0, st>>>(ws.fs, P.labels2, P.B, P.F, P.n_mus, P.grad_mus);
+    CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
+    k_vertex_backward_gather<<<(VP.V + 127) / 128, 128, 0, st>>>(VP, vstart, vcorner, ws.gp6, ws.glen3, grad_verts);
+    CTDR_CUDA(cudaGetLastError(), "k_vertex_backward_gather launch");
     return 0;
 }
 
@@ -479,7 +574,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 16 * 256;
+    return per * (size_t)win + 18 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -515,9 +610,12 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
                                  const int32_t* labels2, const float* mus, int n_mus, int H, int W,
                                  double spacing_x, double spacing_y, double max_sino_val,
                                  const float* grad_im, const float* im, const float* target, double* out2,
-                                 float* grad_verts, float* grad_mus,
+                                 float* grad_verts, float* grad_mus, const int32_t* vadj_start, const int32_t* vadj_corner,
                                  void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                                  cudaStream_t stream) {
+    const bool det = (flags & CTDR_FLAG_DETERMINISTIC) != 0;
+    if (det && (!vadj_start || !vadj_corner))
+        return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
     ProjectWs ws;
     if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
@@ -530,6 +628,12 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
+        if (det) {
+            if (target) { P.target = target + (size_t)b0 * hw; P.out2 = out2; P.mask_hi = (float)(max_sino_val - 1e-6); }
+            else P.grad_im = grad_im + (size_t)b0 * hw;
+            if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, target != nullptr, flags, stream)) return rc;
+            continue;
+        }
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (target) {
@@ -551,6 +655,7 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles, const i
                           const int32_t* labels2, const float* mus, int n_mus, int H, int W,
                           double spacing_x, double spacing_y, double max_sino_val,
                           const float* grad_im, const float* im, float* grad_verts, float* grad_mus,
+                          const int32_t* vadj_start, const int32_t* vadj_corner,
                           void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                           ctdr_stream_t stream) {
     (void)nangles;
@@ -561,7 +666,7 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles, const i
         return fail(CTDR_E_NULL, "ctdr_project_backward: null pointer");
     return project_backward_impl(geom_kind, geom, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
                                  spacing_x, spacing_y, max_sino_val, grad_im, im, nullptr, nullptr,
-                                 grad_verts, grad_mus, workspace, workspace_bytes, stats, flags, stream);
+                                 grad_verts, grad_mus, vadj_start, vadj_corner, workspace, workspace_bytes, stats, flags, stream);
 }
 
 int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -569,6 +674,7 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
                                const int32_t* labels2, const float* mus, int n_mus, int H, int W,
                                double spacing_x, double spacing_y, double max_sino_val,
                                const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                               const int32_t* vadj_start, const int32_t* vadj_corner,
                                void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                                ctdr_stream_t stream) {
     if (int rc = check_geom(geom_kind)) return rc;
@@ -578,6 +684,9 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
         return fail(CTDR_E_NULL, "ctdr_project_residual_step: null pointer");
     // per angle window: vertex stage once, forward raster (phat is an output the caller keeps), then the
     // residual/backward sweep over the same staged p6/len3/ff and face boxes
+    const bool det = (flags & CTDR_FLAG_DETERMINISTIC) != 0;
+    if (det && (!vadj_start || !vadj_corner))
+        return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
     ProjectWs ws;
     if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
@@ -599,6 +708,10 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
         P.mask_hi = (float)(max_sino_val - 1e-6);
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
         P.stats = nullptr;                                   // counters describe the forward sweep only
+        if (det) {
+            if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, true, flags, stream)) return rc;
+            continue;
+        }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
         if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
     }

@@ -127,6 +127,33 @@ class GeometryDevice:
         self.nangles = int(self.table.shape[0])
 
 
+_adjacency_cache: dict = {}
+
+
+def vertex_adjacency(faces_i32, num_verts):
+    """CSR vertex -> incident face corners (3*face + corner), grouped by vertex in ascending corner
+    order (stable sort): what the deterministic backward gathers over.  Cached per faces tensor."""
+    key = (faces_i32.data_ptr(), faces_i32.shape[0], int(num_verts))
+    hit = _adjacency_cache.get(key)
+    if hit is None:
+        flat = faces_i32.reshape(-1).to(torch.int64)
+        order = torch.sort(flat, stable=True).indices.to(torch.int32).contiguous()
+        counts = torch.bincount(flat, minlength=int(num_verts))
+        start = torch.zeros(int(num_verts) + 1, dtype=torch.int32, device=faces_i32.device)
+        start[1:] = torch.cumsum(counts, 0).to(torch.int32)
+        hit = (start.contiguous(), order)
+        _adjacency_cache.clear()
+        _adjacency_cache[key] = hit
+    return hit
+
+
+def _adjacency_ptrs(flags, faces_i32, num_verts):
+    if flags & _lib.FLAG_DETERMINISTIC:
+        start, corner = vertex_adjacency(faces_i32, num_verts)
+        return start.data_ptr(), corner.data_ptr()
+    return None, None
+
+
 def _device_idx(idx_angles, device):
     return torch.as_tensor(idx_angles).to(device=device, dtype=torch.int64).contiguous()
 
@@ -207,14 +234,16 @@ def project_backward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, g
     if grad_mus is None:
         grad_mus = torch.zeros_like(mus)
     L = _lib.lib()
+    flags = default_flags() if flags is None else flags
+    adj0, adj1 = _adjacency_ptrs(flags, faces_i32, V)
     ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 1))
     with torch.cuda.device(dev):
         rc = L.ctdr_project_backward(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                      verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(), mus.data_ptr(),
                                      mus.numel(), geom.H, geom.W, geom.spacing_x, geom.spacing_y,
                                      float(geom.max_sino_val), grad_im.data_ptr(), im.data_ptr(),
-                                     grad_verts.data_ptr(), grad_mus.data_ptr(), ws.data_ptr(), ws.numel(), None,
-                                     default_flags() if flags is None else flags, _lib.stream_ptr(dev))
+                                     grad_verts.data_ptr(), grad_mus.data_ptr(), adj0, adj1, ws.data_ptr(), ws.numel(),
+                                     None, flags, _lib.stream_ptr(dev))
     _lib.check(rc, "ctdr_project_backward")
     return grad_verts, grad_mus
 
@@ -235,15 +264,16 @@ def project_residual_step(geom: GeometryDevice, verts, faces_i32, labels, mus, i
     out2 = torch.zeros(2, dtype=torch.float64, device=dev) if out2 is None else out2
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
+    flags = default_flags() if flags is None else flags
+    adj0, adj1 = _adjacency_ptrs(flags, faces_i32, V)
     ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 1))
     with torch.cuda.device(dev):
         rc = L.ctdr_project_residual_step(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                           verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(),
                                           mus.data_ptr(), mus.numel(), geom.H, geom.W, geom.spacing_x, geom.spacing_y,
                                           float(geom.max_sino_val), target.data_ptr(), phat.data_ptr(),
-                                          grad_verts.data_ptr(), grad_mus.data_ptr(), out2.data_ptr(),
-                                          ws.data_ptr(), ws.numel(), _lib.ptr(stats),
-                                          default_flags() if flags is None else flags, _lib.stream_ptr(dev))
+                                          grad_verts.data_ptr(), grad_mus.data_ptr(), out2.data_ptr(), adj0, adj1,
+                                          ws.data_ptr(), ws.numel(), _lib.ptr(stats), flags, _lib.stream_ptr(dev))
     _lib.check(rc, "ctdr_project_residual_step")
     if want_stats:
         return phat, grad_verts, grad_mus, out2, stats
