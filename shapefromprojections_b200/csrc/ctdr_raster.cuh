@@ -606,8 +606,8 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     // candidate rows: conservative per-row spans (bounding-box rows when the face is degenerate or NaN)
     unsigned rowmask = 0u;
     if (queued) {
-        // spans pay off on larger boxes only; degenerate / NaN faces keep their bounding-box rows
-        const bool tight = (bw * bh >= 8) && (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
+        // degenerate / NaN faces keep their bounding-box rows (measured: spans pay off even on 2x2 boxes)
+        const bool tight = (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
         const SpanSetup sps = span_setup(es);
 #pragma unroll 1
         for (int r = 0; r < bh; ++r) {

@@ -133,18 +133,16 @@ _adjacency_cache: dict = {}
 def vertex_adjacency(faces_i32, num_verts):
     """CSR vertex -> incident face corners (3*face + corner), grouped by vertex in ascending corner
     order (stable sort): what the deterministic backward gathers over.  Cached per faces tensor."""
-    key = (faces_i32.data_ptr(), faces_i32.shape[0], int(num_verts))
-    hit = _adjacency_cache.get(key)
-    if hit is None:
+    hit = _adjacency_cache.get("entry")
+    if hit is None or hit[0] is not faces_i32 or hit[1] != int(num_verts) or hit[2] != faces_i32._version:
         flat = faces_i32.reshape(-1).to(torch.int64)
         order = torch.sort(flat, stable=True).indices.to(torch.int32).contiguous()
         counts = torch.bincount(flat, minlength=int(num_verts))
         start = torch.zeros(int(num_verts) + 1, dtype=torch.int32, device=faces_i32.device)
         start[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        hit = (start.contiguous(), order)
-        _adjacency_cache.clear()
-        _adjacency_cache[key] = hit
-    return hit
+        hit = (faces_i32, int(num_verts), faces_i32._version, start.contiguous(), order)
+        _adjacency_cache["entry"] = hit
+    return hit[3], hit[4]
 
 
 def _adjacency_ptrs(flags, faces_i32, num_verts):
