@@ -385,6 +385,8 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
     if (win > B) win = B;
+    const long long nwin = (B + win - 1) / win;          // equal windows: no small straggler at the end
+    win = (B + nwin - 1) / nwin;
     ws->window = (int)win;
     char* p = static_cast<char*>(base);
     size_t off = 0;
@@ -570,7 +572,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     (void)H; (void)W;
     if (B <= 0 || F <= 0 || V <= 0) return 0;
     const size_t per = project_per_angle_bytes(V, F, need_backward != 0);
-    const size_t budget = (size_t)6 << 30;               // default window budget: 6 GiB
+    const size_t budget = (size_t)8 << 30;               // default window budget: 8 GiB
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;

@@ -476,17 +476,15 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
 // The sinogram stays bit-identical.
 // ------------------------------------------------------------------------------------------
 template <bool EXACT_DIV>
-__device__ __forceinline__ bool cover_slot(const float4 v0, const float4 v1, const float rd, const double2 dy,
+__device__ __forceinline__ bool cover_slot(const float4 v0, const float4 v1, const double2 dy,
                                            float x0, float y0, float& k1, float& k2,
                                            float& w0, float& w1, float& w2) {
-    // diff_fp_for.cu:132-151 bit for bit; prefilter and hoisted quotient as argued in cover_exact
+    // diff_fp_for.cu:132-151 bit for bit (hoisted quotient as argued in DESIGN.md section 5); no prefilter
+    // here: the row spans already leave almost only covered pixels
     const float s = __fsub_rn(x0, v0.x), t = __fsub_rn(y0, v0.y);
     k1 = __fmaf_rn(s, v1.y, -__fmul_rn(v1.x, t));
     k2 = __fmaf_rn(v0.z, t, -__fmul_rn(s, v0.w));
     if (!EXACT_DIV) {
-        const float a1 = k1 * rd, a2 = k2 * rd;
-        if (fminf(a1, a2) < -1e-30f) return false;
-        if ((1.0f - a1) - a2 < -1e-4f * ((1.0f + fabsf(a1)) + fabsf(a2))) return false;
         const double d1 = (double)k1, d2 = (double)k2;
         const double q1 = __dmul_rn(d1, dy.y), q2 = __dmul_rn(d2, dy.y);
         w1 = (float)(k1 == 0.0f ? q1 : __fma_rn(__fma_rn(-q1, dy.x, d1), dy.y, q1));
@@ -518,7 +516,7 @@ __device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int 
             const float4 v0 = sl[0], v1 = sl[1], v3 = sl[3], v4 = sl[4];
             float k1, k2, w0, w1, w2;
             // the face is known to cover the pixel: only the weights are needed again
-            cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
+            cover_slot<EXACT_DIV>(v0, v1, reinterpret_cast<const double2*>(sl)[2],
                                   (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
             const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));
             acc = __fmaf_rn(bary, v4.x, __fmaf_rn(bary, v3.w, acc));
@@ -713,7 +711,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         bool in = false;
         float k1 = 0.0f, k2 = 0.0f, w0, w1, w2;
         if (act) {
-            in = cover_slot<EXACT_DIV>(v0, v1, 0.0f, reinterpret_cast<const double2*>(sl)[2],
+            in = cover_slot<EXACT_DIV>(v0, v1, reinterpret_cast<const double2*>(sl)[2],
                                        (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
             st.cand++;
         }
@@ -777,19 +775,28 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         const unsigned hm[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         const float ov[8] = {old0.x, old0.y, old0.z, old0.w, old1.x, old1.y, old1.z, old1.w};
         unsigned mymask[8];
+        bool anymulti = false;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int pix = (k < 4 ? 0 : 128) + 4 * lane + (k & 3);
             if (P.cnt && hm[k]) S.cntv[pix] += __popc(hm[k]);         // :192
             const bool multi = (hm[k] & (hm[k] - 1u)) != 0u;          // more than one face of the batch
             mymask[k] = multi ? hm[k] : 0u;
-            const unsigned m = __ballot_sync(FULL, multi);
-            if (m) {
-                if (multi) {
-                    S.acc[pix] = ov[k];
-                    S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)pix;
+            anymulti |= multi;
+        }
+        if (__ballot_sync(FULL, anymulti)) {                          // rare: most batches have no such pixel
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int pix = (k < 4 ? 0 : 128) + 4 * lane + (k & 3);
+                const bool multi = mymask[k] != 0u;
+                const unsigned m = __ballot_sync(FULL, multi);
+                if (m) {
+                    if (multi) {
+                        S.acc[pix] = ov[k];
+                        S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)pix;
+                    }
+                    ncp += __popc(m);
                 }
-                ncp += __popc(m);
             }
         }
         if (ncp) {
