@@ -533,11 +533,12 @@ __device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int 
 // every pixel the reference counts lies inside the range; the exact test still decides.
 // Near-zero slopes give no bound.
 struct SpanSetup {
-    float R[3], C[3], M0[3], M1[3];     // root_j = R*t + C ; margin_j = M0 + M1*|t|
-    float lower[3];                     // +1: lower bound on s (a_j > 0), -1: upper bound, 0: unused
+    // x >= RL[j]*t + CL[j] for every j, x <= RU[j]*t + CU[j] for every j   (t = y - ay, x absolute)
+    // unused slots are (0, -3e38) / (0, +3e38); margins and ax are folded into CL / CU
+    float RL[3], CL[3], RU[3], CU[3];
 };
 
-__device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es) {
+__device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es, float tmax) {
     SpanSetup sp;
     const float sg = es.k3 < 0.0f ? -1.0f : 1.0f;
     // a_j*s + beta_j*t + gamma_j >= 0
@@ -548,31 +549,23 @@ __device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es) {
     for (int j = 0; j < 3; ++j) {
         const bool use = fabsf(a[j]) > 1e-4f;
         const float ia = use ? __frcp_rn(a[j]) : 0.0f;
-        sp.R[j] = -beta[j] * ia;
-        sp.C[j] = -gamma[j] * ia;
+        const float R = -beta[j] * ia, C = -gamma[j] * ia;       // root of constraint j on row t: R*t + C
         // rounding of the reference's k1/k2/w0 (~2^-23 of the products involved) and of this estimate
-        // (a few ulp of |root| <= |R||t| + |C|), with a 10x factor, plus 0.02 px
-        sp.M0[j] = 0.02f + 8e-6f * fabsf(sp.C[j]);
-        sp.M1[j] = 8e-6f * fabsf(sp.R[j]);
-        sp.lower[j] = use ? (a[j] > 0.0f ? 1.0f : -1.0f) : 0.0f;
+        // (a few ulp of |root| <= |R||t| + |C|), times 10, plus 0.02 px; worst case over the rows used
+        const float margin = 0.02f + 8e-6f * (fabsf(C) + fabsf(R) * tmax) + 1e-6f * fabsf(es.ax);
+        const bool lower = use && a[j] > 0.0f, upper = use && a[j] < 0.0f;
+        sp.RL[j] = lower ? R : 0.0f; sp.CL[j] = lower ? es.ax + C - margin : -3.0e38f;
+        sp.RU[j] = upper ? R : 0.0f; sp.CU[j] = upper ? es.ax + C + margin : 3.0e38f;
     }
     return sp;
 }
 
-__device__ __forceinline__ bool row_span(const SpanSetup& sp, float ax, float t, int x_lo, int x_hi,
-                                         int& xs, int& xe) {
-    float lo = -3.0e38f, hi = 3.0e38f;
-    const float at = fabsf(t);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const float root = fmaf(sp.R[j], t, sp.C[j]);
-        const float margin = fmaf(sp.M1[j], at, sp.M0[j]);
-        lo = fmaxf(lo, sp.lower[j] > 0.0f ? root - margin : -3.0e38f);
-        hi = fminf(hi, sp.lower[j] < 0.0f ? root + margin : 3.0e38f);
-    }
+__device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo, int x_hi, int& xs, int& xe) {
+    const float lo = fmaxf(fmaxf(fmaf(sp.RL[0], t, sp.CL[0]), fmaf(sp.RL[1], t, sp.CL[1])), fmaf(sp.RL[2], t, sp.CL[2]));
+    const float hi = fminf(fminf(fmaf(sp.RU[0], t, sp.CU[0]), fmaf(sp.RU[1], t, sp.CU[1])), fmaf(sp.RU[2], t, sp.CU[2]));
     // float -> int conversions saturate, so far-away bounds clip correctly
-    xs = max(x_lo, __float2int_ru(ax + lo));
-    xe = min(x_hi, __float2int_rd(ax + hi));
+    xs = max(x_lo, __float2int_ru(lo));
+    xe = min(x_hi, __float2int_rd(hi));
     return xs <= xe;
 }
 
@@ -606,12 +599,12 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     if (queued) {
         // degenerate / NaN faces keep their bounding-box rows (measured: spans pay off even on 2x2 boxes)
         const bool tight = (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
-        const SpanSetup sps = span_setup(es);
+        const SpanSetup sps = span_setup(es, fmaxf(fabsf((float)cy0 - es.ay), fabsf((float)(cy0 + bh - 1) - es.ay)));
 #pragma unroll 1
         for (int r = 0; r < bh; ++r) {
             int xs = cx0, xe = cx0 + bw - 1;
             bool ok = true;
-            if (tight) ok = row_span(sps, es.ax, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe);
+            if (tight) ok = row_span(sps, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe);
             if (ok) {
                 const int rr = cy0 - ty0 + r;
                 rowmask |= 1u << rr;
