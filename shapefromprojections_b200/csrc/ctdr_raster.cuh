@@ -692,6 +692,8 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         lx = min(left, rlen - 1);
     }
     float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
+    float H0 = 0.0f, H1 = 0.0f, H2 = 0.0f;
+    int hkey = -1;                                       // slot of the face this lane finished for earlier lanes
     bool whole = (e == 0);                               // current face entered at its first candidate
 
 #pragma unroll 1
@@ -730,12 +732,10 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
                 lx = 0;
                 if (e == n_i) {
                     if (!IS_FWD) {
-                        if (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f) {
-                            if (whole) {       // entered at its first candidate and finished here: sole contributor
-                                S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
-                            } else {
-                                shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
-                            }
+                        if (whole) {           // entered at its first candidate and finished here: sole contributor
+                            S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
+                        } else {               // this lane finishes a face that earlier lanes started
+                            hkey = i; H0 = M0; H1 = A1; H2 = A2;
                         }
                         M0 = 0.0f; A1 = 0.0f; A2 = 0.0f;
                         whole = true;
@@ -753,8 +753,27 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             }
         }
     }
-    if (!IS_FWD && (M0 != 0.0f || A1 != 0.0f || A2 != 0.0f)) {   // face shared with the following lanes
-        shared_add(&S.mom[0][i], M0); shared_add(&S.mom[1][i], A1); shared_add(&S.mom[2][i], A2);
+    if (!IS_FWD) {
+        // Faces split over several lanes: the lanes that leave a face unfinished hold "tail" partials
+        // (consecutive lanes, same slot); the lane that finishes it holds the "head" partial.  A
+        // segmented shuffle scan sums each run of tails into its last lane; the finishing lane adds
+        // that to its own part and is the face's only writer — no shared-memory atomics.
+        const int tkey = (mycount > 0 && e > 0) ? i : -1;
+        float t0 = M0, t1 = A1, t2 = A2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int kk = __shfl_up_sync(FULL, tkey, d);
+            const float u0 = __shfl_up_sync(FULL, t0, d), u1 = __shfl_up_sync(FULL, t1, d), u2 = __shfl_up_sync(FULL, t2, d);
+            if (lane >= d && kk == tkey && tkey >= 0) { t0 += u0; t1 += u1; t2 += u2; }
+        }
+        const int pk = __shfl_up_sync(FULL, tkey, 1);
+        const float p0 = __shfl_up_sync(FULL, t0, 1), p1 = __shfl_up_sync(FULL, t1, 1), p2 = __shfl_up_sync(FULL, t2, 1);
+        if (hkey >= 0) {
+            const bool chain = lane > 0 && pk == hkey;
+            S.mom[0][hkey] = H0 + (chain ? p0 : 0.0f);
+            S.mom[1][hkey] = H1 + (chain ? p1 : 0.0f);
+            S.mom[2][hkey] = H2 + (chain ? p2 : 0.0f);
+        }
     }
     __syncwarp();
 
