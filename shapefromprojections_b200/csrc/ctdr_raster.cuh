@@ -2,21 +2,24 @@
 // backward (moment-reduced gradients), fused forward+residual+backward.  sm_100a, fp32 + the
 // reference's fp64 barycentric divide.
 //
-// Work decomposition (see DESIGN.md):
-//   angle b  ->  regions of RT x RT tiles (one CTA each)  ->  16x16-pixel tiles (one warp each)
-//   faces    ->  chunks of 32 consecutive faces (one lane each); per (angle, chunk) a pixel
-//                bounding box is precomputed by k_chunk_bbox.
+// Work decomposition (see DESIGN.md section 5):
+//   angle b  ->  super-regions (<= 4x4) -> regions of RT x RT tiles (one CTA each) -> 16x16-pixel
+//                tiles (one warp each, pulled from a CTA-local counter)
+//   faces    ->  chunks of 32 consecutive faces; per (angle, chunk) and per (angle, face) a pixel
+//                bounding box is precomputed by k_chunk_bbox; k_super_lists bins chunks coarsely.
 //   A CTA compacts, IN FACE ORDER, the chunks whose box overlaps its region into a shared-memory
 //   list (ballot + popc ranking); each warp then walks that list for its tile (32 boxes per
-//   ballot); for every overlapping chunk the lanes test their face's precomputed pixel box against
-//   the tile and append the hits, still in face order, to a per-warp queue.  Whenever 32 faces are
-//   queued the warp stages them in shared memory (edge constants, lengths, coefficients) and
-//   spreads their covered bounding-box pixels ("candidates") evenly over its lanes through a
-//   prefix sum, so lane utilisation depends neither on triangle size nor on how many faces of a
-//   chunk touch the tile.  Because lists, chunks, queue and candidates are all visited in
-//   ascending face order and a tile is owned by one warp, every pixel accumulates its faces in
+//   ballot); for every overlapping chunk the lanes test their face's box against the tile and
+//   append the hits, still in face order, to a per-warp queue.  Whenever 32 faces are queued the
+//   warp stages them in shared memory (edge constants, 1/d in fp64, lengths, coefficients, a
+//   conservative pixel span per detector row) and splits the batch's candidate pixels into 32
+//   contiguous ranges, one per lane.  Forward: fragments are applied optimistically while a
+//   per-pixel hit mask records which faces of the batch touched each pixel; pixels touched by more
+//   than one face are restored and recomputed in ascending face order.  Batches, queue and lists are
+//   all in face order and a tile is owned by one warp, so every pixel accumulates its faces in
 //   exactly the order of the reference's per-pixel loop (diff_fp_for.cu:83) -> bit-identical
-//   sinograms, with no global atomics and one coalesced store per pixel.
+//   sinograms, with no global atomics and one coalesced store per pixel.  Backward: per-face
+//   moments in registers, merged across lanes by a segmented shuffle scan, nine RED per (tile, face).
 #pragma once
 #include "ctdr_common.cuh"
 
