@@ -45,9 +45,12 @@ def raster_forward(p6, len3, ff, labels, mus, H, W, max_sino_val, *, want_cnt=Fa
     if p6.shape != (B, F, 6) or len3.shape != (B, F, 3) or ff.numel() != B * F or labels.shape != (F, 2):
         raise RuntimeError("p_bxfx6 / len_bxfx3 / front_facing_bxfx1 / labels_fx2 must be same point size")  # diff_fp.cpp:48-51
     dev = p6.device
+    stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
+    if B == 0 or F == 0:        # empty mesh / no angles: the reference's loops run zero times
+        return (torch.zeros(B, H, W, 1, dtype=torch.float32, device=dev),
+                torch.zeros(B, H, W, 1, dtype=dtype_int, device=dev) if want_cnt else None, stats)
     im = torch.empty(B, H, W, 1, dtype=torch.float32, device=dev)
     cnt = torch.empty(B, H, W, 1, dtype=dtype_int, device=dev) if want_cnt else None
-    stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
     nbytes = L.ctdr_raster_workspace_bytes(B, F, H, W)
     ws = _lib.workspace(dev, nbytes)
@@ -70,6 +73,8 @@ def raster_backward(grad_im, im, p6, len3, ff, labels, mus, max_sino_val, *, fla
     dldf = torch.zeros_like(len3)
     dldmu = torch.zeros_like(mus)
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
+    if B == 0 or F == 0:
+        return (dldp, dldf, dldmu, stats) if want_stats else (dldp, dldf, dldmu)
     L = _lib.lib()
     ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
     with torch.cuda.device(dev):

@@ -208,3 +208,20 @@ def test_hoisted_reciprocal_quotient_is_ieee(cuda_lib):
         _lib.check(cuda_lib.ctdr_selftest_quotient(1 << 31, seed, bad.data_ptr(), _lib.stream_ptr(bad.device)), "selftest")
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+def test_empty_inputs(cuda_lib):
+    """No faces / no angles: zero sinogram, zero gradients (the reference's loops simply do not run)."""
+    from shapefromprojections_b200.function import rasterizer as R
+    lab = torch.zeros(0, 2, dtype=torch.int32, device="cuda"); mus = torch.tensor([0.0, 1.0], device="cuda")
+    im, cnt, _ = R.raster_forward(torch.zeros(2, 0, 6, device="cuda"), torch.zeros(2, 0, 3, device="cuda"),
+                                  torch.zeros(2, 0, 1, device="cuda"), lab, mus, 8, 9, 1.0, want_cnt=True)
+    assert im.shape == (2, 8, 9, 1) and not im.any() and not cnt.any()
+    dp, dl, dm = R.raster_backward(torch.ones(2, 8, 9, 1, device="cuda"), im, torch.zeros(2, 0, 6, device="cuda"),
+                                   torch.zeros(2, 0, 3, device="cuda"), torch.zeros(2, 0, 1, device="cuda"), lab, mus, 1.0)
+    assert dp.shape == (2, 0, 6) and not dm.any()
+    # a mesh entirely off the detector: every face is rejected whole (diff_fp_for.cu:105-106)
+    c = cases.soup_case(8, B=1, F=50, H=32, W=32)
+    c["p6"] = c["p6"] + 1000.0
+    im, cnt, _ = run_forward(c)
+    assert not im.any() and not cnt.any()
