@@ -110,8 +110,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Gpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {wl['desc']}; reference algorithm on host cores, each step = "
-                                   f"a bounded sample ({sample}); pixels are independent in that algorithm"},
+            "config": {"workload": f"{args.config}: {wl['desc']}",
+                       "sample": f"reference algorithm (oracle port) on the host cores; each step = a bounded sample "
+                                 f"({sample}); pixels are independent in that algorithm, so the sample rate is the full-job rate"},
             "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -335,7 +336,9 @@ def main():
                 "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ncu_cfg3_summary.md)"}
     if not args.no_optimise and world == 1:
-        line["optimise_iteration"] = optimise_iteration(torch, args.optimise_iters)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):       # the reference-style modules print; stdout carries the JSON line only
+            line["optimise_iteration"] = optimise_iteration(torch, args.optimise_iters)
     if not args.no_cpu_baseline and world == 1:
         gpix, dt, sample = cpu_reference_sample(wl)
         line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": os.cpu_count(), "kind": "port",

@@ -91,7 +91,8 @@ int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned l
 /* bytes of scratch needed by ctdr_raster_forward / ctdr_raster_backward for these sizes
  * (chunk and face pixel boxes; plus B*F floats used only by the deterministic backward) */
 size_t ctdr_raster_workspace_bytes(int B, int F, int H, int W);
-/* bytes of scratch needed by ctdr_raster_fragments (adds B*H*W cursors only when F > 49152) */
+/* bytes of scratch needed by ctdr_raster_fragments (adds B*H*W cursors only for meshes whose
+ * region chunk lists may need several segments, F > 10240) */
 size_t ctdr_raster_fragments_workspace_bytes(int B, int F, int H, int W);
 
 /* Pass 1 (is_the_first_pass=1): im[B,H,W] = sum over covering faces of
