@@ -204,3 +204,28 @@ def test_deterministic_fused_step_is_bit_reproducible_and_agrees(cuda_lib, kind)
     torch.cuda.synchronize()
     assert torch.equal(d1[0], d2[0]) and torch.equal(d1[1], d2[1])
     assert (d1[0] - ref[0]).norm() <= 2e-5 * ref[0].norm() and (d1[1] - ref[1]).norm() <= 1e-3 * ref[1].norm()
+
+
+def test_size_independent_properties_on_a_larger_case(cuda_lib):
+    """Properties that need no oracle (usable at any size): coverage is invariant under a permutation
+    of the faces (only the summation order changes), the projector is linear in the attenuations,
+    and d(sum im)/d mus equals the per-label partial sinogram sums."""
+    from shapefromprojections_b200 import workloads
+    from shapefromprojections_b200.function import rasterizer as R
+    wl = workloads.make_workload("cfg3_small")
+    gd = R.GeometryDevice(wl["geom"], "cuda")
+    v = dev(wl["verts"]); f32 = dev(wl["faces"], torch.int32); lab = dev(wl["labels"])
+    idx = torch.arange(0, 48, 4, device="cuda")
+    mu_a, mu_b = torch.tensor([0.0, 1.0], device="cuda"), torch.tensor([0.0, 0.37], device="cuda")
+    im_a, cnt_a, st = R.project_forward(gd, v, f32, lab, mu_a, idx, want_cnt=True, want_stats=True)
+    perm = torch.randperm(f32.shape[0], generator=torch.Generator().manual_seed(0)).cuda()
+    im_p, cnt_p, _ = R.project_forward(gd, v, f32[perm].contiguous(), lab[perm].contiguous(), mu_a, idx, want_cnt=True)
+    assert torch.equal(cnt_a, cnt_p)                                   # integer coverage: exact
+    assert int(cnt_a.sum()) == int(st[1])                              # fragments == sum of counts (the reference's vf)
+    assert (im_a - im_p).abs().max() <= 1e-5 * im_a.abs().max() + 4 * 4 * 1e-6
+    im_b, _, _ = R.project_forward(gd, v, f32, lab, mu_b, idx)
+    im_ab, _, _ = R.project_forward(gd, v, f32, lab, mu_a + mu_b, idx)
+    assert (im_ab - (im_a + im_b)).abs().max() <= 2e-5 * im_ab.abs().max()
+    ones = torch.ones_like(im_a)
+    _, gmus = R.project_backward(gd, v, f32, lab, mu_a, idx, ones, im_a)
+    assert abs(gmus[1].item() - im_a.double().sum().item()) <= 1e-4 * im_a.double().sum().item()   # im is linear in mu_1
