@@ -106,6 +106,23 @@ int ctdr_raster_forward(const float* p6, const float* ff, const float* len3,
                         void* workspace, size_t workspace_bytes,
                         int64_t* stats, unsigned flags, ctdr_stream_t stream);
 
+/* n_out (1..CTDR_MAX_OUTPUTS) sinograms in ONE raster pass: the projector is linear in mus
+ * (diff_fp_for.cu:174-190), so renders that differ only in mus share all coverage work — the
+ * 2-3 one-hot renders of Model.estimate_mu (ctdr/model/vanilla.py:186-265) become one pass.
+ *   mus_kxn     [n_out, n_mus]      one attenuation vector per output
+ *   im_kxbxhxw  [n_out, B, H, W]    output k is bit-identical to ctdr_raster_forward with mus_kxn[k]
+ *   target      [B,H,W] or NULL, gram float64 [n_out*n_out + n_out] or NULL (zeroed by the callee):
+ *               gram[i*n_out + j] = sum_pixels im_i*im_j for i <= j (upper triangle),
+ *               gram[n_out*n_out + i] = sum_pixels im_i*target — the normal equations of
+ *               vanilla.py:208-216,245-256, accumulated in float64 while the tiles are on chip. */
+#define CTDR_MAX_OUTPUTS 4
+int ctdr_raster_forward_multi(const float* p6, const float* ff, const float* len3,
+                              const int32_t* labels2, const float* mus_kxn, int n_out, int n_mus,
+                              int B, int F, int H, int W, float max_sino_val,
+                              float* im_kxbxhxw, const float* target, double* gram,
+                              void* workspace, size_t workspace_bytes,
+                              int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
 /* Pass 2 (is_the_first_pass=0): fragment list in the reference's CSR layout, for pixels whose
  * `im` passes the reference's validity test (diff_fp_for.cu:69-73):
  *   imidx_vf[firstidx[pix]+k] = face id + 1, imwei_3vf[3*(firstidx[pix]+k)+{0,1,2}] = (w0,w1,w2),
@@ -175,6 +192,17 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles,
                          float* im, int32_t* cnt,
                          void* workspace, size_t workspace_bytes,
                          int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* Fused projector, n_out sinograms in one pass (see ctdr_raster_forward_multi): what
+ * Model.estimate_mu needs (vanilla.py:186-265) from a single sweep over the mesh. */
+int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles,
+                               const int64_t* idx_angles, int B,
+                               const float* verts, int V, const int32_t* faces, int F,
+                               const int32_t* labels2, const float* mus_kxn, int n_out, int n_mus,
+                               int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                               float* im_kxbxhxw, const float* target, double* gram,
+                               void* workspace, size_t workspace_bytes,
+                               int64_t* stats, unsigned flags, ctdr_stream_t stream);
 
 /* grad_im [B,H,W], im [B,H,W] (forward output) -> ACCUMULATES grad_verts [V,3], grad_mus [n_mus].
  * vadj_start [V+1] / vadj_corner [3F] (int32, may be NULL unless CTDR_FLAG_DETERMINISTIC): for every

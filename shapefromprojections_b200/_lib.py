@@ -30,6 +30,7 @@ SIGNATURES = {
     "ctdr_raster_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ctdr_raster_fragments_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "ctdr_raster_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_raster_forward_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_raster_fragments": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _u, _vp]),
     "ctdr_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_vertex_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "ctdr_project_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "ctdr_project_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
                                   _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_project_forward_multi": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _d, _d, _d,
+                                        _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_project_backward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_project_residual_step": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 using namespace ctdr;
+static_assert(MAX_OUT == CTDR_MAX_OUTPUTS, "kernel and ABI disagree on the output count");
 
 namespace {
 
@@ -99,7 +100,12 @@ template <int MODE>
 int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
     const long long blocks = (long long)P.B * P.regions_x * P.regions_y;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*regions too large for one launch");
-    const size_t smem = raster_smem_bytes(P.n_mus);
+    // after CtaSmem: the CTA's grad_mus accumulators, or (MODE_MULTI) the per-warp normal-equation sums
+    // followed by the tile accumulators of outputs 2 and 3
+    constexpr size_t gram_bytes = (size_t)WARPS * NGRAM * sizeof(double);
+    const size_t smem = (MODE == MODE_MULTI)
+        ? sizeof(CtaSmem) + gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
+        : raster_smem_bytes(P.n_mus);
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate
         CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
@@ -506,6 +512,32 @@ int ctdr_raster_forward(const float* p6, const float* ff, const float* len3, con
     return launch_raster<MODE_FWD>(P, flags, stream);
 }
 
+static int check_multi(int n_out, int n_mus, const float* target, const double* gram) {
+    if (n_out < 1 || n_out > MAX_OUT) return fail(CTDR_E_SHAPE, "n_out=%d outside 1..%d", n_out, MAX_OUT);
+    if (n_mus > 4096) return fail(CTDR_E_SHAPE, "n_mus=%d > 4096", n_mus);
+    if (target && !gram) return fail(CTDR_E_NULL, "target given without gram");
+    return 0;
+}
+
+int ctdr_raster_forward_multi(const float* p6, const float* ff, const float* len3, const int32_t* labels2,
+                              const float* mus_kxn, int n_out, int n_mus, int B, int F, int H, int W,
+                              float max_sino_val, float* im_kxbxhxw, const float* target, double* gram,
+                              void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                              ctdr_stream_t stream) {
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (int rc = check_multi(n_out, n_mus, target, gram)) return rc;
+    if (!p6 || !ff || !len3 || !labels2 || !mus_kxn || !im_kxbxhxw || !workspace) return fail(CTDR_E_NULL, "ctdr_raster_forward_multi: null pointer");
+    RasterWs ws;
+    const size_t need = raster_ws_layout(B, F, H, W, false, false, &ws, workspace);
+    if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+    RasterParams P = base_params(p6, ff, len3, labels2, mus_kxn, n_mus, B, F, H, W, max_sino_val, stats);
+    P.im = im_kxbxhxw; P.n_out = n_out; P.out_stride = (long long)B * H * W; P.target = target; P.gram = gram;
+    if (gram) CTDR_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)(n_out * n_out + n_out), stream), "gram memset");
+    fill_decomposition(P, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
+    if (int rc = launch_chunk_bbox(P, ws.boxes, ws.face_boxes, stream)) return rc;
+    return launch_raster<MODE_MULTI>(P, flags, stream);
+}
+
 int ctdr_raster_fragments(const float* p6, const float* ff, const float* len3, const int32_t* labels2,
                           const float* mus, int n_mus, int B, int F, int H, int W, float max_sino_val,
                           const float* im, const int32_t* firstidx, int32_t* imidx_vf, float* imwei_3vf,
@@ -603,6 +635,38 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
+    }
+    return 0;
+}
+
+int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                               const float* verts, int V, const int32_t* faces, int F,
+                               const int32_t* labels2, const float* mus_kxn, int n_out, int n_mus, int H, int W,
+                               double spacing_x, double spacing_y, double max_sino_val,
+                               float* im_kxbxhxw, const float* target, double* gram,
+                               void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                               ctdr_stream_t stream) {
+    (void)nangles;
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (int rc = check_multi(n_out, n_mus, target, gram)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus_kxn || !im_kxbxhxw || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_project_forward_multi: null pointer");
+    ProjectWs ws;
+    if (int rc = project_ws_layout(B, V, F, H, W, false, workspace, workspace_bytes, &ws)) return rc;
+    if (gram) CTDR_CUDA(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)(n_out * n_out + n_out), stream), "gram memset");
+    const size_t hw = (size_t)H * W;
+    for (int b0 = 0; b0 < B; b0 += ws.window) {
+        const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
+        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus_kxn, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        P.im = im_kxbxhxw + (size_t)b0 * hw; P.n_out = n_out; P.out_stride = (long long)B * (long long)hw;
+        P.target = target ? target + (size_t)b0 * hw : nullptr; P.gram = gram;
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        if (int rc = launch_raster<MODE_MULTI>(P, flags, stream)) return rc;
     }
     return 0;
 }

@@ -25,7 +25,8 @@
 
 namespace ctdr {
 
-enum RasterMode { MODE_FWD = 0, MODE_FRAG = 1, MODE_BWD = 2, MODE_STEP = 3 };
+enum RasterMode { MODE_FWD = 0, MODE_FRAG = 1, MODE_BWD = 2, MODE_STEP = 3, MODE_MULTI = 4 };
+constexpr int MAX_OUT = 4;       // sinograms per MODE_MULTI pass
 
 struct RasterParams {
     // inputs at the Rasterizer boundary (rasterizer.py:13)
@@ -66,6 +67,10 @@ struct RasterParams {
     const float* target;    // [B,H,W]
     float mask_hi;          // float32(max_sino_val - 1e-6), get_valid_mask upper bound (fp_vecs.py:13)
     double* out2;           // {loss_sum, n_valid}
+    // MODE_MULTI: n_out sinograms in one pass; mus is [n_out, n_mus], im is n_out slabs out_stride apart
+    int n_out;
+    long long out_stride;   // elements between consecutive output sinograms
+    double* gram;           // [n_out*n_out + n_out]: sum p_i*p_j (i <= j) and sum p_i*target, or null
     unsigned long long* stats;  // may be null
 };
 
@@ -143,9 +148,10 @@ constexpr int SLOT_VEC = 5;       // float4 per staged face slot (stride 80 B: c
 struct __align__(16) WarpSmem {
     // Staged chunk, array of structures, nonempty faces compacted to the low slots:
     //   v0 = (ax, ay, m, p)   v1 = (n, q, k3, box)   v2 = (d, 1/d) as two doubles
-    //   v3 = (r0, r1, r2, cA) v4 = (cB, excl, 1/k3, lane)
-    // box = lx0 | ly0<<4 | w<<8 | ceil(2^13/w)<<13; excl = exclusive candidate offset of the slot;
-    // cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190).
+    //   v3 = (r0, r1, r2, cA) v4 = (cB, excl, labels/sign word, face id)
+    // box = queue lane | row mask << 5 | (candidates - 1) << 21; excl = exclusive candidate offset of the
+    // slot; cA/cB: forward coefficients +sign*mu_in, -(sign*mu_out') (diff_fp_for.cu:187,190);
+    // labels/sign word (MODE_MULTI): label_in | label_out << 12 | (sign < 0) << 24.
     float4 slot[32 * SLOT_VEC];
     // Per-row pixel spans of the staged faces inside the tile: one byte per (slot, row) =
     // first column << 4 | last column (tile-relative); first > last marks an empty row.
@@ -528,6 +534,69 @@ __device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int 
     }
 }
 
+// MODE_MULTI dynamic shared memory after CtaSmem: per-warp normal-equation sums (NGRAM doubles each),
+// then per-warp tile accumulators of outputs 2 and 3
+constexpr int NGRAM = MAX_OUT * (MAX_OUT + 1) / 2 + MAX_OUT;
+__device__ __forceinline__ float* multi_xacc(float* dyn, int warp) {
+    return reinterpret_cast<float*>(reinterpret_cast<double*>(dyn) + WARPS * NGRAM) + warp * (MAX_OUT - 2) * TILE_PIX;
+}
+
+// MODE_MULTI: accumulator of output k for this warp's tile (k = 0: acc, k = 1: the count array's
+// storage, k >= 2: extra dynamic shared memory)
+__device__ __forceinline__ float* multi_acc(WarpSmem& S, float* xacc, int k) {
+    return k == 0 ? S.acc : (k == 1 ? reinterpret_cast<float*>(S.cntv) : xacc + (k - 2) * TILE_PIX);
+}
+
+// MODE_MULTI: every pixel hit by the batch, pixel-parallel, faces in ascending order; the n_out
+// sinograms share the coverage test and the interpolated length and differ only in the
+// attenuation coefficients, so each of them receives exactly the update sequence of a
+// single-output pass with its own mus (diff_fp_for.cu:174-190).  Returns the non-positive-length count.
+template <bool EXACT_DIV>
+__device__ __noinline__ unsigned redo_multi(WarpSmem& S, float* xacc, const float* __restrict__ mus, int n_mus,
+                                            int n_out, int ncp, int tx0, int ty0, int lane) {
+    unsigned nonpos = 0u;
+#pragma unroll 1
+    for (int base = 0; base < ncp; base += 32) {
+        const bool have = base + lane < ncp;
+        const int pix = have ? (int)S.f.cpix[base + lane] : 0;
+        const int px = pix & 15, py = pix >> 4;
+        float a[MAX_OUT];
+#pragma unroll
+        for (int k = 0; k < MAX_OUT; ++k) a[k] = (k < n_out) ? multi_acc(S, xacc, k)[pix] : 0.0f;
+        unsigned fm = have ? S.f.hitm[pix] : 0u;
+#pragma unroll 1
+        while (fm) {                                          // ascending face id (diff_fp_for.cu:83)
+            const int fi = __ffs(fm) - 1;
+            fm &= fm - 1u;
+            const float4* sl = S.slot + fi * SLOT_VEC;
+            const float4 v0 = sl[0], v1 = sl[1], v3 = sl[3], v4 = sl[4];
+            float k1, k2, w0, w1, w2;
+            cover_slot<EXACT_DIV>(v0, v1, reinterpret_cast<const double2*>(sl)[2],
+                                  (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
+            const float bary = __fmaf_rn(w2, v3.z, __fmaf_rn(w0, v3.x, __fmul_rn(w1, v3.y)));  // :182
+            if (!(bary > 0.0f)) nonpos++;                     // :183 assert -> counter
+            const int word = __float_as_int(v4.z);
+            const int li = word & 0xfff, lo = (word >> 12) & 0xfff;
+            const float sgn = (word >> 24) ? -1.0f : 1.0f;
+#pragma unroll
+            for (int k = 0; k < MAX_OUT; ++k) {
+                if (k < n_out) {
+                    const float mu_in = __ldg(mus + k * n_mus + li);
+                    float mu_out = __ldg(mus + k * n_mus + lo);
+                    if (lo == 0) mu_out = -mu_out;                                     // :174-175
+                    a[k] = __fmaf_rn(bary, -__fmul_rn(sgn, mu_out), __fmaf_rn(bary, __fmul_rn(sgn, mu_in), a[k]));  // :187,190
+                }
+            }
+        }
+        if (have) {
+#pragma unroll
+            for (int k = 0; k < MAX_OUT; ++k) if (k < n_out) multi_acc(S, xacc, k)[pix] = a[k];
+            S.f.hitm[pix] = 0u;
+        }
+    }
+    return nonpos;
+}
+
 // Conservative column range of one face on one detector row (absolute pixels, clipped to [x_lo, x_hi]).
 // Inside <=> sg*k1 >= 0, sg*k2 >= 0, sg*(k1+k2) <= |d| with sg = sign(d) (diff_fp_for.cu:140-151);
 // for a fixed row each is a linear inequality a*s + b(t) >= 0 in s = x - ax with b linear in
@@ -577,6 +646,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
+    constexpr bool IS_MULTI = (MODE == MODE_MULTI);          // gmus doubles as the extra accumulators
     const bool queued = lane < nb;
     const int f = queued ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
@@ -652,10 +722,13 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             cA = __fmul_rn(sgn, mu_in);                               // :187
             cB = -__fmul_rn(sgn, mu_out);                             // :190
             sl[3] = make_float4(r0, r1, r2, cA);
+        } else if (IS_MULTI) {
+            sl[3] = make_float4(r0, r1, r2, 0.0f);
         } else {
             S.mom[0][rank] = 0.0f; S.mom[1][rank] = 0.0f; S.mom[2][rank] = 0.0f;
         }
-        sl[4] = make_float4(cB, __int_as_float(incl - ncand), 0.0f, __int_as_float(f));
+        const int word = lab.x | (lab.y << 12) | (sgn < 0.0f ? 1 << 24 : 0);
+        sl[4] = make_float4(cB, __int_as_float(incl - ncand), __int_as_float(word), __int_as_float(f));
     }
     // forward: snapshot of the 8 pixels this lane checks afterwards (4*lane.. and 128+4*lane..)
     float4 old0 = make_float4(0, 0, 0, 0), old1 = old0;
@@ -723,6 +796,8 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
                 atomicOr(&S.f.hitm[pl], 1u << i);
                 S.acc[pl] = __fmaf_rn(bary, cB, __fmaf_rn(bary, v3.w, S.acc[pl]));               // :187,190
             }
+        } else if (IS_MULTI) {
+            if (in) { st.frag++; atomicOr(&S.f.hitm[pl], 1u << i); }
         } else {
             if (in) {
                 const float g = S.acc[pl];
@@ -734,7 +809,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             if (lx == rlen) {
                 lx = 0;
                 if (e == n_i) {
-                    if (!IS_FWD) {
+                    if (!IS_FWD && !IS_MULTI) {
                         if (whole) {           // entered at its first candidate and finished here: sole contributor
                             S.mom[0][i] = M0; S.mom[1][i] = A1; S.mom[2][i] = A2;
                         } else {               // this lane finishes a face that earlier lanes started
@@ -756,7 +831,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             }
         }
     }
-    if (!IS_FWD) {
+    if (!IS_FWD && !IS_MULTI) {
         // Faces split over several lanes: the lanes that leave a face unfinished hold "tail" partials
         // (consecutive lanes, same slot); the lane that finishes it holds the "head" partial.  A
         // segmented shuffle scan sums each run of tails into its last lane; the finishing lane adds
@@ -779,6 +854,26 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         }
     }
     __syncwarp();
+
+    if (IS_MULTI) {
+        // ---- every pixel hit by the batch is (re)computed pixel-parallel for all outputs -----------
+        const uint4 h0 = *reinterpret_cast<const uint4*>(S.f.hitm + 4 * lane);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(S.f.hitm + 128 + 4 * lane);
+        const unsigned hm[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        int ncp = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool hit = hm[k] != 0u;
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)((k < 4 ? 0 : 128) + 4 * lane + (k & 3));
+            ncp += __popc(m);
+        }
+        __syncwarp();
+        if (ncp) st.nonpos += redo_multi<EXACT_DIV>(S, multi_xacc(gmus, threadIdx.x >> 5), P.mus, P.n_mus,
+                                                    P.n_out, ncp, tx0, ty0, lane);
+        __syncwarp();
+        return;
+    }
 
     if (IS_FWD) {
         // ---- pixels hit by several faces of this batch: restore and redo them in face order --------
@@ -910,6 +1005,11 @@ k_raster(const RasterParams P) {
     constexpr bool K_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
     double loss_acc = 0.0;
     unsigned nvalid_acc = 0u;
+    // MODE_MULTI: after CtaSmem come the per-warp running sums of p_i*p_j (i <= j, row-major upper
+    // triangle) and p_i*target, then the tile accumulators of outputs 2 and 3
+    double* gwarp = reinterpret_cast<double*>(gmus) + warp * NGRAM;
+    float* xacc = multi_xacc(gmus, warp);
+    if (MODE == MODE_MULTI && lane < NGRAM) gwarp[lane] = 0.0;
     if (K_BWD) {
         for (int k = tid; k < P.n_mus; k += THREADS) gmus[k] = 0.0f;
     }
@@ -967,6 +1067,14 @@ k_raster(const RasterParams P) {
                         if (P.cnt) P.cnt[o] = 0;
                     }
                 }
+            } else if (MODE == MODE_MULTI) {
+                for (int o = 0; o < P.n_out; ++o) {
+                    float* dst = P.im + (long long)o * P.out_stride + base;
+                    for (int k = tid; k < rw * rh; k += THREADS) {
+                        const int y = k / rw, x = k - y * rw;
+                        dst[(long long)(ry0 + y) * P.W + rx0 + x] = 0.0f;
+                    }
+                }
             } else if (MODE == MODE_STEP) {
                 if (0.0f <= P.mask_hi) {        // phat == 0 everywhere here: residual = -target
                     const bool vec = ((P.W & 3) == 0) && ((rw & 3) == 0);
@@ -1008,6 +1116,18 @@ k_raster(const RasterParams P) {
                 } else {
                     tile_load<float>(S.acc, P.im, 0.0f, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
                     if (P.cnt) tile_load<int>(S.cntv, P.cnt, 0, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+                }
+            } else if (MODE == MODE_MULTI) {
+#pragma unroll
+                for (int k = 0; k < TILE_PIX / 32; ++k) S.f.hitm[lane + 32 * k] = 0u;
+                for (int o = 0; o < P.n_out; ++o) {
+                    float* a = multi_acc(S, xacc, o);
+                    if (first) {
+#pragma unroll
+                        for (int k = 0; k < TILE_PIX / 32; ++k) a[lane + 32 * k] = 0.0f;
+                    } else {
+                        tile_load<float>(a, P.im + (long long)o * P.out_stride, 0.0f, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+                    }
                 }
             } else if (MODE == MODE_FRAG) {
                 // cursor = fragments already emitted for the pixel; -1 marks pixels the reference
@@ -1107,6 +1227,44 @@ k_raster(const RasterParams P) {
             if (MODE == MODE_FWD) {
                 tile_store<float>(P.im, S.acc, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
                 if (P.cnt) tile_store<int>(P.cnt, S.cntv, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+            } else if (MODE == MODE_MULTI) {
+                for (int o = 0; o < P.n_out; ++o)
+                    tile_store<float>(P.im + (long long)o * P.out_stride, multi_acc(S, xacc, o), b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+                if (last && P.gram) {
+                    // normal-equation sums of Model.estimate_mu (vanilla.py:208-216,245-256) over the finished
+                    // tile: lane partials over 8 pixels in float64, one warp reduction per sum
+                    const long long base = (long long)b * P.H * P.W;
+                    double gs[NGRAM];
+#pragma unroll
+                    for (int g = 0; g < NGRAM; ++g) gs[g] = 0.0;
+#pragma unroll 1
+                    for (int k = 0; k < TILE_PIX / 32; ++k) {
+                        const int pix = lane + 32 * k, row = pix >> 4, col = pix & 15;
+                        float v[MAX_OUT];
+#pragma unroll
+                        for (int o = 0; o < MAX_OUT; ++o) v[o] = (o < P.n_out) ? multi_acc(S, xacc, o)[pix] : 0.0f;
+                        float tg = 0.0f;
+                        if (P.target && ty0 + row <= ty1 && tx0 + col <= tx1)
+                            tg = __ldg(P.target + base + (long long)(ty0 + row) * P.W + tx0 + col);
+                        int g = 0;
+#pragma unroll
+                        for (int i = 0; i < MAX_OUT; ++i) {
+#pragma unroll
+                            for (int j = i; j < MAX_OUT; ++j, ++g) gs[g] = fma((double)v[i], (double)v[j], gs[g]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < MAX_OUT; ++i, ++g) gs[g] = fma((double)v[i], (double)tg, gs[g]);
+                    }
+                    double mine = 0.0;
+#pragma unroll
+                    for (int g = 0; g < NGRAM; ++g) {
+                        double v = gs[g];
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+                        if (lane == g) mine = v;
+                    }
+                    if (lane < NGRAM) gwarp[lane] += mine;
+                }
             } else if (MODE == MODE_FRAG) {
                 if (!last) {   // persist cursors between list segments (cnt doubles as scratch)
 #pragma unroll
@@ -1137,6 +1295,22 @@ k_raster(const RasterParams P) {
         if (lane == 0) {
             if (loss_acc != 0.0) atomicAdd(P.out2 + 0, loss_acc);
             if (nvalid_acc) atomicAdd(P.out2 + 1, (double)nvalid_acc);
+        }
+    }
+    if (MODE == MODE_MULTI && P.gram) {
+        // upper triangle (i <= j) -> gram[i*n_out + j]; right-hand side -> gram[n_out*n_out + i]
+        __syncwarp();
+        if (lane < NGRAM) {
+            const double v = gwarp[lane];
+            int g = 0, dst = -1;
+#pragma unroll
+            for (int i = 0; i < MAX_OUT; ++i) {
+#pragma unroll
+                for (int j = i; j < MAX_OUT; ++j, ++g) if (g == lane && j < P.n_out) dst = i * P.n_out + j;
+            }
+#pragma unroll
+            for (int i = 0; i < MAX_OUT; ++i, ++g) if (g == lane && i < P.n_out) dst = P.n_out * P.n_out + i;
+            if (dst >= 0 && v != 0.0) atomicAdd(P.gram + dst, v);
         }
     }
     if (P.stats) {

@@ -228,6 +228,75 @@ def project_forward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, *,
     return im, cnt, stats
 
 
+def _gram_matrices(gram, K):
+    """(A [K,K] symmetric, rhs [K]) from the callee's upper-triangle layout."""
+    A = gram[:K * K].view(K, K)
+    A = torch.triu(A) + torch.triu(A, 1).T
+    return A, gram[K * K:]
+
+
+def raster_forward_multi(p6, len3, ff, labels, mus_kxn, H, W, max_sino_val, *, target=None, want_gram=False,
+                         want_stats=False, flags=None):
+    """``K = mus_kxn.shape[0]`` sinograms from one raster pass (``ctdr_raster_forward_multi``).
+
+    Returns ``(im [K,B,H,W], A [K,K] | None, rhs [K] | None, stats)``: output ``k`` is bit-identical to
+    ``raster_forward(..., mus_kxn[k])``; ``A[i,j] = sum im_i*im_j`` and ``rhs[i] = sum im_i*target``
+    (float64) are the normal equations of ``Model.estimate_mu`` (``vanilla.py:208-216``).
+    """
+    p6 = _lib.require_cuda_f32(p6, "p_bxfx6")
+    len3 = _lib.require_cuda_f32(len3, "len_bxfx3")
+    ff = _lib.require_cuda_f32(ff, "front_facing_bxfx1")
+    mus_kxn = _lib.require_cuda_f32(mus_kxn, "mus_kxn")
+    B, F, K = p6.shape[0], p6.shape[1], mus_kxn.shape[0]
+    dev = p6.device
+    im = torch.empty(K, B, H, W, dtype=torch.float32, device=dev)
+    want_gram = want_gram or target is not None
+    gram = torch.empty(K * K + K, dtype=torch.float64, device=dev) if want_gram else None
+    if target is not None:
+        target = _lib.require_cuda_f32(target, "target")
+    stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
+    L = _lib.lib()
+    ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
+    with torch.cuda.device(dev):
+        rc = L.ctdr_raster_forward_multi(p6.data_ptr(), ff.data_ptr(), len3.data_ptr(), labels.data_ptr(),
+                                         mus_kxn.data_ptr(), K, mus_kxn.shape[1], B, F, H, W, float(max_sino_val),
+                                         im.data_ptr(), _lib.ptr(target), _lib.ptr(gram), ws.data_ptr(), ws.numel(),
+                                         _lib.ptr(stats), default_flags() if flags is None else flags,
+                                         _lib.stream_ptr(dev))
+    _lib.check(rc, "ctdr_raster_forward_multi")
+    A, rhs = _gram_matrices(gram, K) if want_gram else (None, None)
+    return im, A, rhs, stats
+
+
+def project_forward_multi(geom: GeometryDevice, verts, faces_i32, labels, mus_kxn, idx, *, target=None,
+                          want_gram=False, want_stats=False, flags=None):
+    """Fused projector, ``K`` attenuation vectors in one sweep (``ctdr_project_forward_multi``); see
+    :func:`raster_forward_multi` for the outputs."""
+    dev = verts.device
+    mus_kxn = _lib.require_cuda_f32(mus_kxn, "mus_kxn")
+    B, V, F, K = idx.numel(), verts.shape[0], faces_i32.shape[0], mus_kxn.shape[0]
+    im = torch.empty(K, B, geom.H, geom.W, dtype=torch.float32, device=dev)
+    want_gram = want_gram or target is not None
+    gram = torch.empty(K * K + K, dtype=torch.float64, device=dev) if want_gram else None
+    if target is not None:
+        target = _lib.require_cuda_f32(target, "target")
+        if target.numel() != B * geom.H * geom.W:
+            raise RuntimeError("target must hold B*H*W values")
+    stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
+    L = _lib.lib()
+    ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 0))
+    with torch.cuda.device(dev):
+        rc = L.ctdr_project_forward_multi(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
+                                          verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(),
+                                          mus_kxn.data_ptr(), K, mus_kxn.shape[1], geom.H, geom.W, geom.spacing_x,
+                                          geom.spacing_y, float(geom.max_sino_val), im.data_ptr(), _lib.ptr(target),
+                                          _lib.ptr(gram), ws.data_ptr(), ws.numel(), _lib.ptr(stats),
+                                          default_flags() if flags is None else flags, _lib.stream_ptr(dev))
+    _lib.check(rc, "ctdr_project_forward_multi")
+    A, rhs = _gram_matrices(gram, K) if want_gram else (None, None)
+    return im, A, rhs, stats
+
+
 def project_backward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, grad_im, im, *, flags=None,
                      grad_verts=None, grad_mus=None):
     dev = verts.device

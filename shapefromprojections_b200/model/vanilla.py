@@ -101,23 +101,26 @@ class Model(nn.Module):
 
     def estimate_mu(self, p_cuda):
         """Least-squares attenuations from one-hot renders (``vanilla.py:186-265``): the projector is
-        linear in ``mus``, so p ~= sum_k mu_k * render(e_k); solve the normal equations."""
+        linear in ``mus``, so ``p ~= sum_k mu_k * render(mu_0 = p_min, mu_k = 1)``; the reference renders
+        the mesh once per material and reduces with torch, here the basis sinograms and the normal
+        equations ``A mu = b`` come out of ONE multi-output raster pass (``ctdr_project_forward_multi``)."""
         print("@ estimate mus")
         self.p_min = p_cuda.min()
         n = self.nmaterials
         if n < 3:
             return
         k = n - 1 if n == 3 else 3
-        basis = []
         with torch.no_grad():
             self.mus.data[0] = self.p_min
+            basis_mus = torch.zeros(k, n, dtype=torch.float32, device=self.mus.device)
+            basis_mus[:, 0] = self.p_min
             for j in range(1, k + 1):
-                self.mus.data[1:] = 0
-                self.mus.data[j] = 1
-                basis.append(self.render()[0])
-            A = torch.stack([torch.stack([(a * b).sum() for b in basis]) for a in basis]).to(self.dtype).cpu()
-            rhs = torch.stack([(a * p_cuda).sum() for a in basis]).to(self.dtype).cpu()
-            est = torch.pinverse(A).matmul(rhs)
+                basis_mus[j - 1, j] = 1.0
+            idx = torch.arange(self.nangles, device=self.vertices.device)
+            _, A, rhs = self.fp.forward_multi(self.get_displaced_vertices(), self.faces, idx, basis_mus,
+                                              target=p_cuda.to(torch.float32).contiguous())
+            est = torch.pinverse(A.to(self.dtype).cpu()).matmul(rhs.to(self.dtype).cpu())
+            self.mus.data[1:] = 0
             for j in range(1, k + 1):
                 self.mus.data[j] = est[j - 1]
 

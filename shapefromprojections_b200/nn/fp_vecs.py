@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
-from ..function.rasterizer import GeometryDevice, ProjectMesh, Rasterizer, VertexStage
+from ..function.rasterizer import GeometryDevice, ProjectMesh, Rasterizer, VertexStage, project_forward_multi
 
 
 def get_valid_mask(phat, max_val):
@@ -72,6 +72,18 @@ class _ProjectorBase(nn.Module):
                                 self.max_sino_val, backprop)
         phat = im.squeeze()                                                      # fp_vecs.py:203 (B==1 drops the axis)
         return phat, get_valid_mask(phat, self.max_sino_val)
+
+
+    @torch.no_grad()
+    def forward_multi(self, verts_vx3, faces_fx3, idx_angles, mus_kxn, target=None):
+        """``K`` renders that differ only in ``mus`` from ONE sweep over the mesh (no gradients):
+        ``(phat [K,B,H,W], A [K,K], rhs [K])`` with ``A[i,j] = sum phat_i*phat_j`` and
+        ``rhs[i] = sum phat_i*target`` in float64 — what ``Model.estimate_mu`` (``vanilla.py:186-265``)
+        obtains from 2-3 full renders plus torch reductions."""
+        idx = idx_angles.to(device=self.labels_fx2.device, dtype=torch.int64).contiguous()
+        im, A, rhs, _ = project_forward_multi(self.geom, verts_vx3.detach().contiguous(), self._faces32(faces_fx3),
+                                              self.labels_fx2, mus_kxn, idx, target=target, want_gram=True)
+        return im, A, rhs
 
 
 class FP(_ProjectorBase):

@@ -131,7 +131,7 @@ assert xch.scalars.tolist() == [2.0 * tot, 70.0]
 gv, gm, loss = xch.mean_gradients()
 assert abs(loss.item() - 2.0 * tot / 70.0) < 1e-12 and torch.allclose(gv, torch.full((V, 3), tot / 70.0))
 dist.barrier(); dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank {{rank}} ok\n"); sys.stdout.flush()
 """
 
 
