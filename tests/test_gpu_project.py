@@ -229,3 +229,64 @@ def test_size_independent_properties_on_a_larger_case(cuda_lib):
     ones = torch.ones_like(im_a)
     _, gmus = R.project_backward(gd, v, f32, lab, mu_a, idx, ones, im_a)
     assert abs(gmus[1].item() - im_a.double().sum().item()) <= 1e-4 * im_a.double().sum().item()   # im is linear in mu_1
+
+
+def test_full_size_config3_properties(cuda_lib):
+    """BASELINE.json config 3 in full (cone 720 x 1024 x 1024, torus of 100k triangles, 7.5e8 pixels) —
+    far beyond what the oracle can check, so through properties that hold at any size:
+    angles are independent (a strided shard reproduces its slices of the full run bit for bit — what the
+    multi-GPU sharding relies on), coverage is invariant under a face permutation, the projector is linear
+    in the attenuations, the fused residual step reports exactly the masked-L2 of its own sinogram, and
+    gradients add up over angle shards."""
+    from shapefromprojections_b200 import workloads
+    from shapefromprojections_b200.function import rasterizer as R
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~60 GB of device memory")
+    wl = workloads.make_workload("cfg3")
+    gd = R.GeometryDevice(wl["geom"], "cuda")
+    v = dev(wl["verts"]); f32 = dev(wl["faces"], torch.int32); lab = dev(wl["labels"])
+    B = wl["nangles"]
+    idx = torch.arange(B, device="cuda")
+    mu_a, mu_b = torch.tensor([0.0, 1.0], device="cuda"), torch.tensor([0.0, 0.37], device="cuda")
+    im_a, cnt_a, st = R.project_forward(gd, v, f32, lab, mu_a, idx, want_cnt=True, want_stats=True)
+    assert int(cnt_a.sum(dtype=torch.int64)) == int(st[1]) and int(st[0]) == 0          # vf; no non-positive length
+    # chords of the torus: at most 2*sqrt((R+r)^2 - (R-r)^2) = 1.358 (cone magnification adds a little); the
+    # few knife-edge pixels where only one of the two surfaces is counted are what get_valid_mask removes
+    odd = (im_a < -1e-4) | (im_a > 1.5)
+    assert int(odd.sum()) <= 1e-5 * im_a.numel()
+    del odd
+    # angle independence (strided shard of 8 ranks, rank 3)
+    shard = idx[3::8].contiguous()
+    im_s, cnt_s, _ = R.project_forward(gd, v, f32, lab, mu_a, shard, want_cnt=True)
+    assert torch.equal(im_s, im_a[3::8]) and torch.equal(cnt_s, cnt_a[3::8])
+    del im_s, cnt_s
+    # face permutation: integer coverage exact, sinogram within the reordering tolerance (SURVEY 8a)
+    perm = torch.randperm(f32.shape[0], generator=torch.Generator().manual_seed(0)).cuda()
+    im_p, cnt_p, _ = R.project_forward(gd, v, f32[perm].contiguous(), lab[perm].contiguous(), mu_a, idx, want_cnt=True)
+    assert torch.equal(cnt_a, cnt_p)
+    assert float((im_a - im_p).abs().max()) <= 1e-5 * float(im_a.abs().max()) + 4 * 4 * 1e-6
+    del im_p, cnt_p, cnt_a
+    # linearity in mus
+    im_b, _, _ = R.project_forward(gd, v, f32, lab, mu_b, idx)
+    im_ab, _, _ = R.project_forward(gd, v, f32, lab, mu_a + mu_b, idx)
+    assert float((im_ab - (im_a + im_b)).abs().max()) <= 2e-5 * float(im_ab.abs().max())
+    del im_b, im_ab
+    # fused residual step: loss / count are those of its own sinogram; gradients add over shards
+    vt = v * dev(workloads.TARGET_SCALE)
+    target, _, _ = R.project_forward(gd, vt, f32, lab, mu_a, idx)
+    phat, gv, gm, out2 = R.project_residual_step(gd, v, f32, lab, mu_a, idx, target)
+    assert torch.equal(phat, im_a)
+    mask = (phat > -1e-6) & (phat <= gd.max_sino_val - 1e-6)
+    assert int(out2[1].item()) == int(mask.sum())
+    ref_loss = ((target - phat).double() ** 2)[mask].sum().item()
+    assert abs(out2[0].item() - ref_loss) <= 1e-9 * ref_loss
+    del mask, phat
+    gv_sum, gm_sum, loss_sum = torch.zeros_like(gv), torch.zeros_like(gm), 0.0
+    for r in range(2):
+        sh = idx[r::2].contiguous()
+        _, gvr, gmr, o2 = R.project_residual_step(gd, v, f32, lab, mu_a, sh, target[r::2].contiguous())
+        gv_sum += gvr; gm_sum += gmr; loss_sum += o2[0].item()
+    assert abs(loss_sum - out2[0].item()) <= 1e-9 * out2[0].item()
+    assert float((gv_sum - gv).norm()) <= 1e-4 * float(gv.norm()) and float((gm_sum - gm).norm()) <= 1e-4 * float(gm.norm())
+    assert float(gv.norm()) > 0
