@@ -654,6 +654,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1, bh = 1;
+    float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0, ffv = 0.0f;
     if (queued) {
         const short4 fb = __ldg(P.face_box + bf);
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
@@ -663,6 +664,9 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
         bw = min((int)fb.z, tx1) - cx0 + 1;
         bh = min((int)fb.w, ty1) - cy0 + 1;
+        const float* pl = P.len3 + bf * 3;              // in flight while the spans are computed
+        r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
+        ffv = __ldg(P.ff + bf);
     }
     __syncwarp();                                       // queue entries consumed
     const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
@@ -701,7 +705,6 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     }
     const int T = __shfl_sync(FULL, incl, 31);
 
-    float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
     if (mine) {
         float4* sl = S.slot + rank * SLOT_VEC;
         // box word: queue lane (5 bits) | row mask (16 bits) << 5 | (ncand - 1) << 21   (ncand <= 256)
@@ -710,9 +713,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         sl[1] = make_float4(es.n, es.q, es.k3, __int_as_float(box));
         const double d = (double)es.k3 + 1e-15;                        // diff_fp_for.cu:144 denominator
         reinterpret_cast<double2*>(sl)[2] = make_double2(d, 1.0 / d);
-        const float* pl = P.len3 + bf * 3;
-        r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
-        if (__ldg(P.ff + bf) < 0.0f) sgn = -1.0f;                     // diff_fp_for.cu:94-96
+        if (ffv < 0.0f) sgn = -1.0f;                                  // diff_fp_for.cu:94-96
         if (lab.x == lab.y) sgn = -sgn;                               // :167-169
         float cA = 0.0f, cB = 0.0f;
         if (IS_FWD) {
@@ -1198,16 +1199,28 @@ k_raster(const RasterParams P) {
                         lb += 32;
                         continue;
                     }
+                    // two hit chunks per turn: both face-box loads are in flight before either is tested
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
+                    const int src2 = m ? __ffs(m) - 1 : -1;
                     const int f = __shfl_sync(FULL, cid, src) * CHUNK + lane;
-                    short4 fb = make_short4(BOX_EMPTY_LO, BOX_EMPTY_LO, -1, -1);
+                    const int f2 = __shfl_sync(FULL, cid, max(src2, 0)) * CHUNK + lane;
+                    short4 fb = make_short4(BOX_EMPTY_LO, BOX_EMPTY_LO, -1, -1), fb2 = fb;
                     if (f < P.F) fb = __ldg(P.face_box + (long long)b * P.F + f);
+                    if (src2 >= 0 && f2 < P.F) fb2 = __ldg(P.face_box + (long long)b * P.F + f2);
                     const bool fh = box_overlap(fb, tx0, ty0, tx1, ty1);
                     const unsigned hm = __ballot_sync(FULL, fh);
                     if (lane == 0) st.hits += (hm != 0u);
                     if (fh) S.qface[qn + __popc(hm & lanemask_lt())] = f;
                     qn += __popc(hm);
+                    if (src2 >= 0 && qn < 32) {                // room for another 32: take the second chunk too
+                        m &= m - 1;
+                        const bool fh2 = box_overlap(fb2, tx0, ty0, tx1, ty1);
+                        const unsigned hm2 = __ballot_sync(FULL, fh2);
+                        if (lane == 0) st.hits += (hm2 != 0u);
+                        if (fh2) S.qface[qn + __popc(hm2 & lanemask_lt())] = f2;
+                        qn += __popc(hm2);
+                    }
                     __syncwarp();
                 }
                 if (qn == 0) break;
