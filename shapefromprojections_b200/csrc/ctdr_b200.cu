@@ -62,7 +62,7 @@ int pick_region_tiles(int B, int F, int H, int W) {
     return rt;
 }
 
-size_t raster_smem_bytes(int n_mus) { return sizeof(CtaSmem) + (size_t)n_mus * sizeof(float); }
+size_t raster_smem_bytes(int n_mus) { return (size_t)n_mus * sizeof(float); }   // dynamic part; CtaSmem is static
 
 constexpr int MAX_SR = 4;   // super-regions per detector edge
 
@@ -100,17 +100,17 @@ template <int MODE>
 int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
     const long long blocks = (long long)P.B * P.regions_x * P.regions_y;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*regions too large for one launch");
-    // after CtaSmem: the CTA's grad_mus accumulators, or (MODE_MULTI) the per-warp normal-equation sums
-    // followed by the tile accumulators of outputs 2 and 3
+    // dynamic shared memory: the CTA's grad_mus accumulators, or (MODE_MULTI) the per-warp normal-equation
+    // sums followed by the tile accumulators of outputs 2 and 3; with the static CtaSmem it stays below the
+    // 48 KB that need no opt-in (n_mus <= 4096)
+    static_assert(sizeof(CtaSmem) + 4096 * sizeof(float) <= 48 * 1024, "static + dynamic shared memory");
     constexpr size_t gram_bytes = (size_t)WARPS * NGRAM * sizeof(double);
     const size_t smem = (MODE == MODE_MULTI)
-        ? sizeof(CtaSmem) + gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
+        ? gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
         : raster_smem_bytes(P.n_mus);
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate
-        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else {
-        CTDR_CUDA(cudaFuncSetAttribute(k_raster<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
         k_raster<MODE, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     }
     CTDR_CUDA(cudaGetLastError(), "k_raster launch");

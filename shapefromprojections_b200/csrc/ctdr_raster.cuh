@@ -176,7 +176,7 @@ struct CtaSmem {
     int    list_n;
     int    next_tile;
     WarpSmem warp[WARPS];
-    // followed by float gmus[n_mus] (dynamic)
+    // the dynamic shared memory holds float gmus[n_mus] (backward modes) or the MODE_MULTI extras
 };
 
 __device__ __forceinline__ bool box_overlap(const short4 bx, int x0, int y0, int x1, int y1) {
@@ -605,18 +605,20 @@ __device__ __noinline__ unsigned redo_multi(WarpSmem& S, float* xacc, const floa
 // every pixel the reference counts lies inside the range; the exact test still decides.
 // Near-zero slopes give no bound.
 struct SpanSetup {
-    // x >= RL[j]*t + CL[j] for every j, x <= RU[j]*t + CU[j] for every j   (t = y - ay, x absolute)
-    // unused slots are (0, -3e38) / (0, +3e38); margins and ax are folded into CL / CU
-    float RL[3], CL[3], RU[3], CU[3];
+    // x >= RL_k*t + CL_k and x <= RU_k*t + CU_k for k = 0, 1   (t = y - ay, x absolute).  The three edge
+    // coefficients a_j sum to zero, so at most two edges bound the row from the left and at most two from
+    // the right; unused slots are (0, -3e38) / (0, +3e38); margins and ax are folded into CL / CU.
+    float RL0, CL0, RL1, CL1, RU0, CU0, RU1, CU1;
 };
 
 __device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es, float tmax) {
-    SpanSetup sp;
+    SpanSetup sp = {0.0f, -3.0e38f, 0.0f, -3.0e38f, 0.0f, 3.0e38f, 0.0f, 3.0e38f};
     const float sg = es.k3 < 0.0f ? -1.0f : 1.0f;
     // a_j*s + beta_j*t + gamma_j >= 0
     const float a[3] = {sg * es.q, -sg * es.p, -sg * (es.q - es.p)};
     const float beta[3] = {-sg * es.n, sg * es.m, -sg * (es.m - es.n)};
     const float gamma[3] = {0.0f, 0.0f, fabsf(es.k3)};
+    bool have_l = false, have_u = false;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const bool use = fabsf(a[j]) > 1e-4f;
@@ -626,15 +628,17 @@ __device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es, float tmax)
         // (a few ulp of |root| <= |R||t| + |C|), times 10, plus 0.02 px; worst case over the rows used
         const float margin = 0.02f + 8e-6f * (fabsf(C) + fabsf(R) * tmax) + 1e-6f * fabsf(es.ax);
         const bool lower = use && a[j] > 0.0f, upper = use && a[j] < 0.0f;
-        sp.RL[j] = lower ? R : 0.0f; sp.CL[j] = lower ? es.ax + C - margin : -3.0e38f;
-        sp.RU[j] = upper ? R : 0.0f; sp.CU[j] = upper ? es.ax + C + margin : 3.0e38f;
+        const float cl = es.ax + C - margin, cu = es.ax + C + margin;
+        if (lower && !have_l) { sp.RL0 = R; sp.CL0 = cl; } else if (lower) { sp.RL1 = R; sp.CL1 = cl; }
+        if (upper && !have_u) { sp.RU0 = R; sp.CU0 = cu; } else if (upper) { sp.RU1 = R; sp.CU1 = cu; }
+        have_l |= lower; have_u |= upper;
     }
     return sp;
 }
 
 __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo, int x_hi, int& xs, int& xe) {
-    const float lo = fmaxf(fmaxf(fmaf(sp.RL[0], t, sp.CL[0]), fmaf(sp.RL[1], t, sp.CL[1])), fmaf(sp.RL[2], t, sp.CL[2]));
-    const float hi = fminf(fminf(fmaf(sp.RU[0], t, sp.CU[0]), fmaf(sp.RU[1], t, sp.CU[1])), fmaf(sp.RU[2], t, sp.CU[2]));
+    const float lo = fmaxf(fmaf(sp.RL0, t, sp.CL0), fmaf(sp.RL1, t, sp.CL1));
+    const float hi = fminf(fmaf(sp.RU0, t, sp.CU0), fmaf(sp.RU1, t, sp.CU1));
     // float -> int conversions saturate, so far-away bounds clip correctly
     xs = max(x_lo, __float2int_ru(lo));
     xe = min(x_hi, __float2int_rd(hi));
@@ -985,9 +989,11 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 template <int MODE, bool EXACT_DIV>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
+    // fixed-size state in STATIC shared memory (addresses are link-time constants: no base pointer to keep
+    // or rebuild in the hot loops); the dynamic part holds grad_mus accumulators / MODE_MULTI extras
+    __shared__ CtaSmem C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CtaSmem& C = *reinterpret_cast<CtaSmem*>(smem_raw);
-    float* gmus = reinterpret_cast<float*>(smem_raw + sizeof(CtaSmem));
+    float* gmus = reinterpret_cast<float*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int regions = P.regions_x * P.regions_y;
