@@ -72,6 +72,7 @@ struct RasterParams {
     long long out_stride;   // elements between consecutive output sinograms
     double* gram;           // [n_out*n_out + n_out]: sum p_i*p_j (i <= j) and sum p_i*target, or null
     unsigned long long* stats;  // may be null
+    int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
 };
 
 // ------------------------------------------------------------------------------------------
@@ -645,7 +646,7 @@ __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo,
     return xs <= xe;
 }
 
-template <int MODE, bool EXACT_DIV>
+template <int MODE, bool EXACT_DIV, bool DIRECT>
 __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
@@ -675,12 +676,89 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     __syncwarp();                                       // queue entries consumed
     const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
 
+    if (lane == 0) st.visits++;
+    if (ffv < 0.0f) sgn = -1.0f;                                      // diff_fp_for.cu:94-96
+    if (lab.x == lab.y) sgn = -sgn;                                   // :167-169
+    // degenerate / NaN faces keep their bounding-box rows (measured: spans pay off even on 2x2 boxes)
+    const bool tight = (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
+    const SpanSetup sps = span_setup(es, fmaxf(fabsf((float)cy0 - es.ay), fabsf((float)(cy0 + bh - 1) - es.ay)));
+    float4 old0 = make_float4(0, 0, 0, 0), old1 = old0;   // forward: snapshot of the 8 pixels this lane checks afterwards
+    float fm0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;             // backward: moments of this lane's face
+    bool mine = false;
+    int rank = lane;                                      // slot (and hit-mask bit) of this lane's face
+
+    // ---- direct walk: every face of the batch is small, so each lane walks the row spans of its OWN face
+    // with the face constants in registers — no candidate redistribution (prefix sums, slot search, span
+    // bytes in shared memory), no merging of partial moments.  The walk takes max-over-lanes steps, which
+    // for small boxes is cheaper than that machinery (config 3: 8 steps on average, fine meshes: 2).
+    const bool direct = DIRECT && !IS_MULTI && __reduce_max_sync(FULL, queued ? bw * bh : 0) <= P.direct_max_box;
+    if (direct) {
+        mine = queued;
+        const double d = (double)es.k3 + 1e-15;                       // diff_fp_for.cu:144 denominator
+        const double2 dy = make_double2(d, 1.0 / d);
+        const float4 v0 = make_float4(es.ax, es.ay, es.m, es.p), v1 = make_float4(es.n, es.q, es.k3, 0.0f);
+        float cA = 0.0f, cB = 0.0f;
+        if (IS_FWD) {
+            if (queued) {
+                const float mu_in = __ldg(P.mus + lab.x);
+                float mu_out = __ldg(P.mus + lab.y);
+                if (lab.y == 0) mu_out = -mu_out;                     // :174-175
+                cA = __fmul_rn(sgn, mu_in);                           // :187
+                cB = -__fmul_rn(sgn, mu_out);                         // :190
+                // the fix-up of pixels hit by several faces re-reads the faces from their slots (slot = lane)
+                float4* sl = S.slot + lane * SLOT_VEC;
+                sl[0] = v0; sl[1] = v1;
+                reinterpret_cast<double2*>(sl)[2] = dy;
+                sl[3] = make_float4(r0, r1, r2, cA);
+                sl[4] = make_float4(cB, 0.0f, 0.0f, __int_as_float(f));
+            }
+            old0 = *reinterpret_cast<const float4*>(S.acc + 4 * lane);
+            old1 = *reinterpret_cast<const float4*>(S.acc + 128 + 4 * lane);
+            __syncwarp();
+        }
+        int r = -1, x = 0, xe = -1;
+        bool active = queued;
+#pragma unroll 1
+        while (active) {                                              // first non-empty row
+            if (++r >= bh) { active = false; break; }
+            int xs = cx0; xe = cx0 + bw - 1;
+            if (!tight || row_span(sps, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe)) { x = xs; break; }
+        }
+#pragma unroll 1
+        while (__any_sync(FULL, active)) {
+            if (active) {
+                float k1, k2, w0, w1, w2;
+                const bool in = cover_slot<EXACT_DIV>(v0, v1, dy, (float)x, (float)(cy0 + r), k1, k2, w0, w1, w2);
+                st.cand++;
+                if (in) {
+                    const int pl = (cy0 + r - ty0) * TILE + (x - tx0);
+                    if (IS_FWD) {
+                        const float bary = __fmaf_rn(w2, r2, __fmaf_rn(w0, r0, __fmul_rn(w1, r1)));       // :182
+                        if (!(bary > 0.0f)) st.nonpos++;              // :183 assert -> counter
+                        st.frag++;
+                        atomicOr(&S.f.hitm[pl], 1u << lane);
+                        S.acc[pl] = __fmaf_rn(bary, cB, __fmaf_rn(bary, cA, S.acc[pl]));                  // :187,190
+                    } else {
+                        const float g = S.acc[pl];
+                        if (g != 0.0f) { st.frag++; fm0 += g; fa1 = fmaf(g, k1, fa1); fa2 = fmaf(g, k2, fa2); }
+                    }
+                }
+                if (++x > xe) {                                       // next non-empty row of this face
+#pragma unroll 1
+                    while (true) {
+                        if (++r >= bh) { active = false; break; }
+                        int xs = cx0; xe = cx0 + bw - 1;
+                        if (!tight || row_span(sps, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe)) { x = xs; break; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+    // ---- general path: candidates of the whole batch redistributed evenly over the lanes ------------
     // candidate rows: conservative per-row spans (bounding-box rows when the face is degenerate or NaN)
     unsigned rowmask = 0u;
     if (queued) {
-        // degenerate / NaN faces keep their bounding-box rows (measured: spans pay off even on 2x2 boxes)
-        const bool tight = (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
-        const SpanSetup sps = span_setup(es, fmaxf(fabsf((float)cy0 - es.ay), fabsf((float)(cy0 + bh - 1) - es.ay)));
 #pragma unroll 1
         for (int r = 0; r < bh; ++r) {
             int xs = cx0, xe = cx0 + bw - 1;
@@ -695,11 +773,10 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         }
     }
     const unsigned nz = __ballot_sync(FULL, ncand > 0);
-    if (lane == 0) st.visits++;
     if (nz == 0u) return;
-    const bool mine = ncand > 0;
+    mine = ncand > 0;
     const int nslots = __popc(nz);
-    const int rank = __popc(nz & lanemask_lt());
+    rank = __popc(nz & lanemask_lt());
 
     int incl = ncand;
 #pragma unroll
@@ -717,8 +794,6 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         sl[1] = make_float4(es.n, es.q, es.k3, __int_as_float(box));
         const double d = (double)es.k3 + 1e-15;                        // diff_fp_for.cu:144 denominator
         reinterpret_cast<double2*>(sl)[2] = make_double2(d, 1.0 / d);
-        if (ffv < 0.0f) sgn = -1.0f;                                  // diff_fp_for.cu:94-96
-        if (lab.x == lab.y) sgn = -sgn;                               // :167-169
         float cA = 0.0f, cB = 0.0f;
         if (IS_FWD) {
             const float mu_in = __ldg(P.mus + lab.x);
@@ -735,8 +810,6 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         const int word = lab.x | (lab.y << 12) | (sgn < 0.0f ? 1 << 24 : 0);
         sl[4] = make_float4(cB, __int_as_float(incl - ncand), __int_as_float(word), __int_as_float(f));
     }
-    // forward: snapshot of the 8 pixels this lane checks afterwards (4*lane.. and 128+4*lane..)
-    float4 old0 = make_float4(0, 0, 0, 0), old1 = old0;
     if (IS_FWD) {
         old0 = *reinterpret_cast<const float4*>(S.acc + 4 * lane);
         old1 = *reinterpret_cast<const float4*>(S.acc + 128 + 4 * lane);
@@ -859,6 +932,8 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         }
     }
     __syncwarp();
+    if (!IS_FWD && !IS_MULTI && mine) { fm0 = S.mom[0][rank]; fa1 = S.mom[1][rank]; fa2 = S.mom[2][rank]; }
+    }   // general path
 
     if (IS_MULTI) {
         // ---- every pixel hit by the batch is (re)computed pixel-parallel for all outputs -----------
@@ -928,7 +1003,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
 
     if (mine) {
         // per-face gradients from the moments of this tile's fragments (face_grads_from_moments)
-        const float m0 = S.mom[0][rank], a1 = S.mom[1][rank], a2 = S.mom[2][rank];
+        const float m0 = fm0, a1 = fa1, a2 = fa2;
         if (m0 != 0.0f || a1 != 0.0f || a2 != 0.0f) {
             const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
             const float cgeo = sgn * (mu_in - mu_out);                // raw mu, no label-0 flip (back.cu:115)
@@ -986,7 +1061,7 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // ------------------------------------------------------------------------------------------
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool EXACT_DIV>
+template <int MODE, bool EXACT_DIV, bool DIRECT = false>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
     // fixed-size state in STATIC shared memory (addresses are link-time constants: no base pointer to keep
@@ -1232,7 +1307,7 @@ k_raster(const RasterParams P) {
                 if (qn == 0) break;
                 const int nbatch = min(qn, 32);
                 if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
-                else process_batch_blocked<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                else process_batch_blocked<MODE, EXACT_DIV, DIRECT>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
                 const int rest = qn - nbatch;                  // < 32: shift the tail to the front
                 int tf = 0;
                 if (lane < rest) tf = S.qface[32 + lane];
