@@ -108,14 +108,17 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
     const size_t smem = (MODE == MODE_MULTI)
         ? gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
         : raster_smem_bytes(P.n_mus);
+    const bool stats = P.stats != nullptr;
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else if ((MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP) && P.direct_max_box > 0) {
         // fine meshes (about a pixel per face): batches of small boxes are walked face-per-lane
         constexpr int M = (MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP) ? MODE : MODE_FWD;
-        k_raster<M, false, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        if (stats) k_raster<M, false, true, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        else k_raster<M, false, true, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else {
-        k_raster<MODE, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        if (stats) k_raster<MODE, false, false, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        else k_raster<MODE, false, false, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     }
     CTDR_CUDA(cudaGetLastError(), "k_raster launch");
     return 0;

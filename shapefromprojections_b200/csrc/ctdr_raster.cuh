@@ -232,13 +232,26 @@ __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, flo
     gp[4] = G0 * (c10 * d1n + c20 * d2n); gp[5] = G0 * (c10 * d1q + c20 * d2q);
 }
 
-struct ThreadStats {
-    unsigned int cand, frag, nonpos, visits, hits;   // visits/hits: (tile, chunk) pairs staged / with candidates
+// counter that compiles to nothing: the statistics are optional (`stats` may be NULL) and five live
+// registers per thread are worth more to the hot loops than to a caller who does not read them
+struct NoCount {
+    __device__ __forceinline__ NoCount& operator++() { return *this; }
+    __device__ __forceinline__ NoCount operator++(int) { return *this; }
+    template <typename T> __device__ __forceinline__ NoCount& operator+=(T) { return *this; }
+    __device__ __forceinline__ operator unsigned() const { return 0u; }
+};
+template <bool ON> struct CountType { typedef unsigned int type; };
+template <> struct CountType<false> { typedef NoCount type; };
+
+template <bool STATS>
+struct ThreadStatsT {
+    typedef typename CountType<STATS>::type count_t;
+    count_t cand{}, frag{}, nonpos{}, visits{}, hits{};   // visits/hits: batches staged / (tile, chunk) pairs with an overlapping face
     // Attenuation gradient: each lane keeps a running sum per (label_in, label_out) pair and only
     // touches the CTA's shared accumulators when its face's labels change (meshes carry long runs
     // of equal labels), instead of two contended shared-memory atomics per (tile, face).
-    int lab_in, lab_out;
-    float sum_in, sum_out;
+    int lab_in = 0, lab_out = 0;
+    float sum_in = 0.0f, sum_out = 0.0f;
     __device__ __forceinline__ void mus_flush(float* gmus) {
         if (sum_in != 0.0f) shared_add(gmus + lab_in, sum_in);
         if (sum_out != 0.0f) shared_add(gmus + lab_out, sum_out);
@@ -253,7 +266,7 @@ struct ThreadStats {
 // ------------------------------------------------------------------------------------------
 // one (tile, chunk): stage the chunk's faces, spread candidates over lanes, evaluate coverage
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool EXACT_DIV>
+template <int MODE, bool EXACT_DIV, class ThreadStats>
 __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S, float* gmus,
                                               int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                               int lane, ThreadStats& st) {
@@ -646,7 +659,7 @@ __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo,
     return xs <= xe;
 }
 
-template <int MODE, bool EXACT_DIV, bool DIRECT>
+template <int MODE, bool EXACT_DIV, bool DIRECT, class ThreadStats>
 __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
@@ -966,10 +979,13 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         const float ov[8] = {old0.x, old0.y, old0.z, old0.w, old1.x, old1.y, old1.z, old1.w};
         unsigned mymask[8];
         bool anymulti = false;
+        if (P.cnt) {                                                  // coverage counts are optional
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (hm[k]) S.cntv[(k < 4 ? 0 : 128) + 4 * lane + (k & 3)] += __popc(hm[k]);   // :192
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int pix = (k < 4 ? 0 : 128) + 4 * lane + (k & 3);
-            if (P.cnt && hm[k]) S.cntv[pix] += __popc(hm[k]);         // :192
             const bool multi = (hm[k] & (hm[k] - 1u)) != 0u;          // more than one face of the batch
             mymask[k] = multi ? hm[k] : 0u;
             anymulti |= multi;
@@ -1061,7 +1077,7 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // ------------------------------------------------------------------------------------------
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool EXACT_DIV, bool DIRECT = false>
+template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
     // fixed-size state in STATIC shared memory (addresses are link-time constants: no base pointer to keep
@@ -1082,7 +1098,7 @@ k_raster(const RasterParams P) {
     const int* super = P.slist + sidx * P.NC;
     const int nsuper = __ldg(P.scount + sidx);
     WarpSmem& S = C.warp[warp];
-    ThreadStats st = {0u, 0u, 0u, 0u, 0u, 0, 0, 0.0f, 0.0f};
+    ThreadStatsT<STATS> st;
 
     constexpr bool K_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
     double loss_acc = 0.0;
@@ -1407,7 +1423,7 @@ k_raster(const RasterParams P) {
             if (dst >= 0 && v != 0.0) atomicAdd(P.gram + dst, v);
         }
     }
-    if (P.stats) {
+    if (STATS && P.stats) {
         const unsigned cand = __reduce_add_sync(FULL, st.cand);
         const unsigned frag = __reduce_add_sync(FULL, st.frag);
         const unsigned nonpos = __reduce_add_sync(FULL, st.nonpos);
