@@ -43,6 +43,7 @@ int check_sizes(int B, int F, int H, int W, int n_mus) {
         return fail(CTDR_E_SHAPE, "sizes must be positive (B=%d F=%d H=%d W=%d n_mus=%d)", B, F, H, W, n_mus);
     if (H > 32767 || W > 32767) return fail(CTDR_E_SHAPE, "detector larger than 32767 pixels (H=%d W=%d)", H, W);
     if (n_mus > 4096) return fail(CTDR_E_SHAPE, "n_mus=%d > 4096", n_mus);
+    if ((F + CHUNK - 1) / CHUNK > (1 << 20)) return fail(CTDR_E_SHAPE, "F=%d > %d faces", F, CHUNK << 20);   // region list entries hold 20-bit chunk ids
     return 0;
 }
 

@@ -172,7 +172,9 @@ struct __align__(16) WarpSmem {
 };
 
 struct CtaSmem {
-    int    list_id[LIST_CAP];     // chunks overlapping the region, ascending (boxes are re-read through L1)
+    // chunks overlapping the region, ascending: chunk id (20 bits) | first/last tile column and first/last
+    // tile row of its box inside the region (3 bits each), so a tile tests a chunk without touching memory
+    int    list_id[LIST_CAP];
     int    wsum[WARPS];
     int    list_n;
     int    next_tile;
@@ -1122,7 +1124,14 @@ k_raster(const RasterParams P) {
             const int cpos = c + tid;
             bool hit = false;
             int ci = 0;
-            if (cpos < nsuper) { ci = __ldg(super + cpos); hit = box_overlap(__ldg(boxes + ci), rx0, ry0, rx1, ry1); }
+            if (cpos < nsuper) {
+                ci = __ldg(super + cpos);
+                const short4 bx = __ldg(boxes + ci);
+                hit = box_overlap(bx, rx0, ry0, rx1, ry1);
+                const int c0 = max((int)bx.x - rx0, 0) >> 4, c1 = min(((int)bx.z - rx0) >> 4, 7);
+                const int w0 = max((int)bx.y - ry0, 0) >> 4, w1 = min(((int)bx.w - ry0) >> 4, 7);
+                ci |= (c0 << 20) | (c1 << 23) | (w0 << 26) | (w1 << 29);
+            }
             const unsigned m = __ballot_sync(FULL, hit);
             if (lane == 0) C.wsum[warp] = __popc(m);
             __syncthreads();
@@ -1200,7 +1209,8 @@ k_raster(const RasterParams P) {
             if (lane == 0) tix = atomicAdd(&C.next_tile, 1);
             tix = __shfl_sync(FULL, tix, 0);
             if (tix >= ntiles) break;
-            const int tx0 = rx0 + (tix % P.RT) * TILE, ty0 = ry0 + (tix / P.RT) * TILE;
+            const unsigned tcol = (unsigned)(tix % P.RT), trow = (unsigned)(tix / P.RT);
+            const int tx0 = rx0 + (int)tcol * TILE, ty0 = ry0 + (int)trow * TILE;
             if (tx0 > rx1 || ty0 > ry1) continue;
             const int tx1 = min(tx0 + TILE - 1, rx1), ty1 = min(ty0 + TILE - 1, ry1);
 
@@ -1291,7 +1301,11 @@ k_raster(const RasterParams P) {
                         if (lb >= nlist) { exhausted = true; break; }
                         const int e = lb + lane;
                         bool hit = false;
-                        if (e < nlist) { cid = C.list_id[e]; hit = box_overlap(__ldg(boxes + cid), tx0, ty0, tx1, ty1); }
+                        if (e < nlist) {
+                            const unsigned w = (unsigned)C.list_id[e];
+                            cid = (int)(w & 0xfffffu);
+                            hit = (tcol >= ((w >> 20) & 7u)) & (tcol <= ((w >> 23) & 7u)) & (trow >= ((w >> 26) & 7u)) & (trow <= (w >> 29));
+                        }
                         m = __ballot_sync(FULL, hit);
                         lb += 32;
                         continue;
