@@ -211,12 +211,21 @@ __device__ __forceinline__ void seg_reduce3(int key, int lane, float (&v)[3]) {
 // and the cancellation the reference suffers in fp32 (-t*k3 + p*k1) is avoided.
 // grad_len (:126-136) and the interpolated length (:143-147) use sum g*w_k = A_k/d.
 // cgeo = sign*(mu_in - mu_out): the two label iterations of back.cu:111 merged.
+// fp64 reciprocal to ~2^-40 (hardware seed + one Newton step): the backward is specified to a relative
+// tolerance, so its three per-face fp64 divisions need not be IEEE-rounded
+__device__ __forceinline__ double fast_rcp64(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    return y * fma(-d, y, 2.0);
+}
+
 __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, float r0, float r1, float r2,
                                                         float cgeo, float M0, float A1, float A2,
                                                         float gp[6], float gl[3], float& bsum) {
     const float k3 = es.k3;
     const double dd = (double)k3 + 1e-15;
-    const float W1 = (float)((double)A1 / dd), W2 = (float)((double)A2 / dd);
+    const double ydd = fast_rcp64(dd);
+    const float W1 = (float)((double)A1 * ydd), W2 = (float)((double)A2 * ydd);
     const float W0 = M0 - W1 - W2;                            // sum g*w_k
     gl[0] = cgeo * W0; gl[1] = cgeo * W1; gl[2] = cgeo * W2;
     bsum = r0 * W0 + r1 * W1 + r2 * W2;
@@ -227,7 +236,7 @@ __device__ __forceinline__ void face_grads_from_moments(const EdgeSetup& es, flo
     const float d1s = es.q * k3 * M0,    d2s = -es.p * k3 * M0;
     const float d1t = -es.n * k3 * M0,   d2t = es.m * k3 * M0;
     const float c10 = r1 - r0, c20 = r2 - r0;                 // back.cu:271-280
-    const float G0 = (float)((double)cgeo / ((double)(k3 * k3) + 1e-15));       // back.cu:282-283
+    const float G0 = (float)((double)cgeo * fast_rcp64((double)(k3 * k3) + 1e-15));   // back.cu:282-283
     gp[0] = -G0 * (c10 * (d1m + d1n + d1s) + c20 * (d2m + d2n + d2s));          // back.cu:246-258
     gp[1] = -G0 * (c10 * (d1p + d1q + d1t) + c20 * (d2p + d2q + d2t));
     gp[2] = G0 * (c10 * d1m + c20 * d2m); gp[3] = G0 * (c10 * d1p + c20 * d2p);
