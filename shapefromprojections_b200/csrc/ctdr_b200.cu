@@ -80,12 +80,14 @@ void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face
     P.nsr_y = (P.regions_y + P.sr_ry - 1) / P.sr_ry;
 }
 
-int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, cudaStream_t st) {
-    const long long warps = (long long)P.B * P.NC;
-    const long long blocks = (warps + WARPS - 1) / WARPS;
-    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
-    k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
-    CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
+int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, cudaStream_t st, bool have_boxes = false) {
+    if (!have_boxes) {      // the fused path gets both box arrays from k_face_assemble
+        const long long warps = (long long)P.B * P.NC;
+        const long long blocks = (warps + WARPS - 1) / WARPS;
+        if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+        k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
+        CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
+    }
     if (P.slist) {      // tile-binned modes: coarse (super-region) lists for phase A of k_raster
         const long long sblocks = (long long)P.B * P.nsr_x * P.nsr_y;
         if (sblocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B too large for one launch");
@@ -404,6 +406,7 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
     if (win > B) win = B;
+    if (win > 65535) win = 65535;                        // k_face_assemble puts the angle in gridDim.y
     const long long nwin = (B + win - 1) / win;          // equal windows: no small straggler at the end
     win = (B + nwin - 1) / nwin;
     ws->window = (int)win;
@@ -433,12 +436,15 @@ int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* 
     return 0;
 }
 
-int launch_vertex_forward_staged(const VertexParams& P, float4* vt, float* p6, float* len3, float* ff, cudaStream_t st) {
-    const long long nv = (long long)P.B * P.V, nf = (long long)P.B * P.F;
-    if ((nv + 255) / 256 > 0x7fffffffLL || (nf + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+// vertex stage of one angle window in the fused path; also produces the face and chunk pixel boxes
+int launch_vertex_forward_staged(const VertexParams& P, float4* vt, const int32_t* labels2, float* p6, float* len3, float* ff,
+                                 short4* face_boxes, short4* chunk_boxes, cudaStream_t st) {
+    const long long nv = (long long)P.B * P.V;
+    if ((nv + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*V too large for one launch");
+    if (P.B > 65535) return fail(CTDR_E_SHAPE, "angle window of %d angles > 65535", P.B);
     k_vertex_transform<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(P, vt);
     CTDR_CUDA(cudaGetLastError(), "k_vertex_transform launch");
-    k_face_assemble<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(P, vt, p6, len3, ff);
+    k_face_assemble<<<dim3((unsigned)((P.F + 255) / 256), (unsigned)P.B), 256, 0, st>>>(P, vt, labels2, p6, len3, ff, face_boxes, chunk_boxes);
     CTDR_CUDA(cudaGetLastError(), "k_face_assemble launch");
     return 0;
 }
@@ -641,12 +647,12 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im + (size_t)b0 * hw;
         P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
-        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
     }
     return 0;
@@ -673,12 +679,12 @@ int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, co
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus_kxn, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im_kxbxhxw + (size_t)b0 * hw; P.n_out = n_out; P.out_stride = (long long)B * (long long)hw;
         P.target = target ? target + (size_t)b0 * hw : nullptr; P.gram = gram;
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
-        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         if (int rc = launch_raster<MODE_MULTI>(P, flags, stream)) return rc;
     }
     return 0;
@@ -701,7 +707,7 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
         CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
@@ -714,7 +720,7 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
             continue;
         }
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
-        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         if (target) {
             P.target = target + (size_t)b0 * hw;
             P.out2 = out2;
@@ -772,10 +778,10 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, ws.p6, ws.len3, ws.ff, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
-        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream)) return rc;
+        if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         P.im = phat + (size_t)b0 * hw;
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");

@@ -164,12 +164,17 @@ k_vertex_transform(const VertexParams P, float4* __restrict__ vt) {
     vt[gid] = make_float4(o.px, o.py, o.len, o.cx);
 }
 
+// grid = (ceil(F / 256), B): a warp holds 32 consecutive faces of ONE angle, i.e. exactly one chunk of the
+// raster kernels, so the per-face pixel boxes and the chunk box (k_chunk_bbox's job at the Rasterizer
+// boundary) come out of the same pass while the projected vertices are still in registers.
 __global__ void __launch_bounds__(256)
-k_face_assemble(const VertexParams P, const float4* __restrict__ vt, float* __restrict__ p6,
-                float* __restrict__ len3, float* __restrict__ ff) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)P.B * P.F) return;
-    const int b = (int)(gid / P.F), f = (int)(gid % P.F);
+k_face_assemble(const VertexParams P, const float4* __restrict__ vt, const int* __restrict__ labels2,
+                float* __restrict__ p6, float* __restrict__ len3, float* __restrict__ ff,
+                short4* __restrict__ face_box, short4* __restrict__ chunk_box) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    int x0 = BOX_EMPTY_LO, y0 = BOX_EMPTY_LO, x1 = -1, y1 = -1;
+    if (f < P.F) {
+    const long long gid = (long long)b * P.F + f;
     const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
     const float4* row = vt + (long long)b * P.V;
     const float4 a = __ldg(row + i0), bb = __ldg(row + i1), c = __ldg(row + i2);
@@ -201,6 +206,19 @@ k_face_assemble(const VertexParams P, const float4* __restrict__ vt, float* __re
     o[0] = make_float2(a.x, a.y); o[1] = make_float2(bb.x, bb.y); o[2] = make_float2(c.x, c.y);
     len3[gid * 3 + 0] = a.z; len3[gid * 3 + 1] = bb.z; len3[gid * 3 + 2] = c.z;
     ff[gid] = facing;
+    const int2 lab = __ldg(reinterpret_cast<const int2*>(labels2) + f);
+    int ix0, iy0, ix1, iy1;
+    if (lab.x >= lab.y && face_int_bbox(a.x, a.y, bb.x, bb.y, c.x, c.y, P.H, P.W, ix0, iy0, ix1, iy1)) {   // as k_chunk_bbox
+        x0 = ix0; y0 = iy0; x1 = ix1; y1 = iy1;
+    }
+    face_box[gid] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+    }
+    // blockDim.x is a multiple of 32 and chunks start at multiples of 32: one warp == one chunk
+    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
+    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
+    const int chunk = f >> 5, nchunks = (P.F + 31) >> 5;
+    if ((threadIdx.x & 31) == 0 && chunk < nchunks)
+        chunk_box[(long long)b * nchunks + chunk] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
 }
 
 // cotangent of one vertex: (gpx, gpy, glen) -> d/d(x,y,z), hand-written reverse mode of
