@@ -647,7 +647,7 @@ __device__ __forceinline__ SpanSetup span_setup(const EdgeSetup& es, float tmax)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const bool use = fabsf(a[j]) > 1e-4f;
-        const float ia = use ? __frcp_rn(a[j]) : 0.0f;
+        const float ia = use ? __fdividef(1.0f, a[j]) : 0.0f;       // MUFU.RCP: ~1 ulp, far inside the margin below
         const float R = -beta[j] * ia, C = -gamma[j] * ia;       // root of constraint j on row t: R*t + C
         // rounding of the reference's k1/k2/w0 (~2^-23 of the products involved) and of this estimate
         // (a few ulp of |root| <= |R||t| + |C|), times 10, plus 0.02 px; worst case over the rows used
