@@ -783,16 +783,18 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     // candidate rows: conservative per-row spans (bounding-box rows when the face is degenerate or NaN)
     unsigned rowmask = 0u;
     if (queued) {
+        unsigned char* sprow = &S.span[lane][cy0 - ty0];
+        const int pack0 = -(tx0 << 4) - tx0;                           // ((xs - tx0) << 4) | (xe - tx0) == (xs << 4) + xe + pack0
+        unsigned bit = 1u << (cy0 - ty0);
 #pragma unroll 1
-        for (int r = 0; r < bh; ++r) {
+        for (int r = 0; r < bh; ++r, bit <<= 1) {
             int xs = cx0, xe = cx0 + bw - 1;
             bool ok = true;
             if (tight) ok = row_span(sps, (float)(cy0 + r) - es.ay, cx0, cx0 + bw - 1, xs, xe);
             if (ok) {
-                const int rr = cy0 - ty0 + r;
-                rowmask |= 1u << rr;
+                rowmask |= bit;
                 ncand += xe - xs + 1;
-                S.span[lane][rr] = (unsigned char)(((xs - tx0) << 4) | (xe - tx0));
+                sprow[r] = (unsigned char)((xs << 4) + xe + pack0);
             }
         }
     }
@@ -1304,6 +1306,7 @@ k_raster(const RasterParams P) {
             int qn = 0, lb = 0, cid = 0;
             unsigned m = 0u;
             bool exhausted = false;
+            const short4* fbrow = P.face_box + (long long)b * P.F;
             while (true) {
                 while (qn < 32 && !exhausted) {
                     if (m == 0u) {
@@ -1326,8 +1329,8 @@ k_raster(const RasterParams P) {
                     const int f = __shfl_sync(FULL, cid, src) * CHUNK + lane;
                     const int f2 = __shfl_sync(FULL, cid, max(src2, 0)) * CHUNK + lane;
                     short4 fb = make_short4(BOX_EMPTY_LO, BOX_EMPTY_LO, -1, -1), fb2 = fb;
-                    if (f < P.F) fb = __ldg(P.face_box + (long long)b * P.F + f);
-                    if (src2 >= 0 && f2 < P.F) fb2 = __ldg(P.face_box + (long long)b * P.F + f2);
+                    if (f < P.F) fb = __ldg(fbrow + f);
+                    if (src2 >= 0 && f2 < P.F) fb2 = __ldg(fbrow + f2);
                     const bool fh = box_overlap(fb, tx0, ty0, tx1, ty1);
                     const unsigned hm = __ballot_sync(FULL, fh);
                     if (lane == 0) st.hits += (hm != 0u);
