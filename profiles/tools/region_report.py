@@ -1,68 +1,85 @@
-"""Per-region instruction / stall-sample shares of k_raster from an ncu report (uses sass_by_line)."""
-import csv, io, subprocess, sys, os
+"""Share of executed warp-instructions and stall samples per part of k_raster, from an ncu report that was
+captured with --import-source on (joins the SASS page with `nvdisasm -g` line info, see sass_by_line.py).
+
+    python profiles/tools/region_report.py <report.ncu-rep> <libctdr_b200.so> <ctdr_raster.cuh>
+"""
+import os
+import sys
 from collections import defaultdict
+
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import sass_by_line as S
+import sass_by_line as S  # noqa: E402
+
+# (first source line containing the marker) -> region name; regions run until the next marker
+MARKERS = [
+    ("__device__ __forceinline__ bool box_overlap(", "box tests (chunk / face boxes vs tile)"),
+    ("__device__ __forceinline__ void seg_reduce3(", "backward: moments -> per-face gradients"),
+    ("struct NoCount {", "statistics / grad_mus cache"),
+    ("__device__ __forceinline__ void process_batch(const RasterParams& P", "ordered walk (fragment-list mode)"),
+    ("__device__ __forceinline__ bool cover_slot(", "exact coverage test (fp64 quotient)"),
+    ("__device__ __noinline__ void redo_conflicted(", "forward fix-up of multiply-hit pixels"),
+    ("__device__ __forceinline__ float* multi_xacc(", "multi-output pass"),
+    ("struct SpanSetup {", "row spans: set-up"),
+    ("__device__ __forceinline__ bool row_span(", "row spans: per row"),
+    ("__device__ __forceinline__ void process_batch_blocked(", "batch: face loads + edge set-up"),
+    ("    // ---- direct walk:", "batch: direct walk (fine-mesh variant)"),
+    ("    // ---- general path:", "row spans: row loop"),
+    ("    const unsigned nz = __ballot_sync(FULL, ncand > 0);", "batch: prefix sums, slot staging, range search"),
+    ("    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;", "candidate loop (walk + accumulate)"),
+    ("        // Faces split over several lanes:", "backward: merge of partial moments"),
+    ("    if (IS_MULTI) {\n", "hit-mask check / fix-up / per-face RED"),
+    ("// tile load / store helpers", "tile loads / stores"),
+    ("k_raster(const RasterParams P) {", "kernel prologue + shared-address rebuilds"),
+    ("        // ---- phase A:", "phase A (region list) + empty regions"),
+    ("        // ---- phase B:", "tile dispatch + prologue"),
+    ("            // walk the region's chunk list", "list walk + face queue"),
+    ("            // tile epilogue", "tile epilogue + kernel tail"),
+]
+
 
 def main(rep, lib, src_path):
-    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt))); hdr = rows[0]
-    keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-            'smsp__issue_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
-            'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
-            'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-            'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__warps_eligible.avg.per_cycle_active',
-            'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
-            'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
-            'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct']
-    ni = hdr.index('Kernel Name')
-    print('kernels:', [r[ni][:40] for r in rows[2:]])
-    for k in keys:
-        if k in hdr:
-            i = hdr.index(k); print(f'{k:90s}', [r[i] for r in rows[2:]])
-    src = open(src_path).read().split('\n')
-    def find(tag): return next(i + 1 for i, l in enumerate(src) if tag in l)
-    marks = [('1 batch setup', find('__device__ __forceinline__ void process_batch(')),
-             ('2 cand decode + slot loads', find('for (int base = 0; base < T; base += 32)')),
-             ('3 cand coverage', find('// coverage: diff_fp_for.cu:132-151')),
-             ('4 cand accumulate', find('if (act) st.cand++;')),
-             ('5 bwd per-face epilogue', find('if (IS_BWD && mine) {')),
-             ('6 tile load/store', find('// tile load / store helpers')),
-             ('7 phase A + empty fill', find('k_raster(const RasterParams P)')),
-             ('8 tile dispatch + prologue', find('// ---- phase B')),
-             ('9 list walk + enqueue', find("// walk the region's chunk list")),
-             ('a tile epilogue / sync / flush', find('// tile epilogue'))]
-    first = marks[0][1]
+    text = open(src_path).read()
+    src = text.split("\n")
+    bounds = []
+    for marker, name in MARKERS:
+        key = marker.split("\n")[0]
+        line = next((i + 1 for i, l in enumerate(src) if key in l), None)
+        if line is None:
+            raise SystemExit(f"marker not found: {marker!r}")
+        bounds.append((line, name))
+    bounds.sort()
+
     def region(key):
-        if key is None: return 'unknown'
+        if key is None:
+            return "unattributed"
         f, l = key
-        if f == 'ctdr_common.cuh': return 'common (edge_setup etc.)'
-        if f != 'ctdr_raster.cuh': return f
-        if l < first: return '0 helpers (seg reduce, grads, bbox kernel)'
-        name = marks[0][0]
-        for n, ln in marks:
-            if l >= ln: name = n
+        if f != os.path.basename(src_path):
+            return {"ctdr_common.cuh": "edge set-up / helpers (ctdr_common.cuh)"}.get(f, "intrinsics headers (shuffles, ballots, loads, atomics)")
+        name = "header"
+        for ln, n in bounds:
+            if l >= ln:
+                name = n
         return name
-    for ksub_ncu, ksub in (('k_raster<(int)0', 'k_rasterILi0ELb0'), ('k_raster<(int)3', 'k_rasterILi3ELb0')):
+
+    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0", "k_rasterILi0ELb0ELb0ELb0"),
+                           ("k_raster<(int)3, (bool)0, (bool)0, (bool)0", "k_rasterILi3ELb0ELb0ELb0")):
         try:
             blk = S.ncu_rows(rep, ksub_ncu)
         except SystemExit:
             continue
         sass = S.sass_lines(lib, ksub)
-        h = blk['hdr']; ie = h.index('Instructions Executed'); sm = h.index('# Samples')
-        regions = defaultdict(lambda: [0, 0]); tot = [0, 0]
-        for r, s in zip(blk['rows'], sass):
-            k = region(s[2]); regions[k][0] += int(r[ie]); regions[k][1] += int(r[sm]); tot[0] += int(r[ie]); tot[1] += int(r[sm])
-        print(blk['name'], 'warp-inst', tot[0], 'samples', tot[1], '(sass rows', len(blk['rows']), len(sass), ')')
-        for k, (i, s) in sorted(regions.items()):
-            print(f'  {k:45s} inst {100*i/tot[0]:6.2f}%  samples {100*s/tot[1]:6.2f}%')
+        h = blk["hdr"]
+        ie, sm = h.index("Instructions Executed"), h.index("# Samples")
+        regions = defaultdict(lambda: [0, 0])
+        tot = [0, 0]
+        for r, s in zip(blk["rows"], sass):
+            k = region(s[2])
+            regions[k][0] += int(r[ie]); regions[k][1] += int(r[sm])
+            tot[0] += int(r[ie]); tot[1] += int(r[sm])
+        print(f"{blk['name']}: {tot[0]:.4g} warp-instructions, {tot[1]} stall samples ({len(blk['rows'])} SASS instructions)")
+        for k, (i, s) in sorted(regions.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:58s} inst {100 * i / tot[0]:6.2f} %   samples {100 * s / tot[1]:6.2f} %")
 
-if __name__ == '__main__':
+
+if __name__ == "__main__":
     main(sys.argv[1], sys.argv[2], sys.argv[3])
