@@ -72,6 +72,7 @@ struct RasterParams {
     long long out_stride;   // elements between consecutive output sinograms
     double* gram;           // [n_out*n_out + n_out]: sum p_i*p_j (i <= j) and sum p_i*target, or null
     unsigned long long* stats;  // may be null
+    int region_major;       // CTA order, see k_raster
     int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
 };
 
@@ -1101,8 +1102,11 @@ k_raster(const RasterParams P) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int regions = P.regions_x * P.regions_y;
-    const int b = (int)(blockIdx.x / (unsigned)regions);
-    const int rr = (int)(blockIdx.x % (unsigned)regions);
+    // CTA order: angle-major (neighbouring regions of one angle run together and share its face data in
+    // L2), or region-major (all angles of a region together: the last CTAs of the launch are then the
+    // detector's bottom rows, usually empty — no heavy CTA is left running alone at the end of a small grid)
+    const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
+    const int rr = P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions);
     const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
     const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
     const short4* boxes = P.chunk_box + (long long)b * P.NC;
