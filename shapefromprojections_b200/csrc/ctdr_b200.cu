@@ -74,7 +74,7 @@ void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
     P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
     P.chunk_box = boxes;
-    P.region_major = 0;
+    P.region_major = 1;     // measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3)
     if (const char* env = getenv("CTDR_REGION_MAJOR")) P.region_major = atoi(env) != 0;
     P.sr_rx = (P.regions_x + MAX_SR - 1) / MAX_SR;
     P.sr_ry = (P.regions_y + MAX_SR - 1) / MAX_SR;
