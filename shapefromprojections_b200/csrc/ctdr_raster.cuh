@@ -7,10 +7,12 @@
 //                tiles (one warp each, pulled from a CTA-local counter)
 //   faces    ->  chunks of 32 consecutive faces; per (angle, chunk) and per (angle, face) a pixel
 //                bounding box is precomputed by k_chunk_bbox; k_super_lists bins chunks coarsely.
+//                (the fused projector gets both box arrays from k_face_assemble, ctdr_vertex.cuh)
 //   A CTA compacts, IN FACE ORDER, the chunks whose box overlaps its region into a shared-memory
-//   list (ballot + popc ranking); each warp then walks that list for its tile (32 boxes per
-//   ballot); for every overlapping chunk the lanes test their face's box against the tile and
-//   append the hits, still in face order, to a per-warp queue.  Whenever 32 faces are queued the
+//   list (ballot + popc ranking; each entry = chunk id + the chunk's tile range inside the region);
+//   each warp then walks that list for its tile (32 entries per ballot, bit tests only); for every
+//   overlapping chunk the lanes test their face's box against the tile and append the hits, still
+//   in face order, to a per-warp queue.  Whenever 32 faces are queued the
 //   warp stages them in shared memory (edge constants, 1/d in fp64, lengths, coefficients, a
 //   conservative pixel span per detector row) and splits the batch's candidate pixels into 32
 //   contiguous ranges, one per lane.  Forward: fragments are applied optimistically while a
@@ -20,6 +22,9 @@
 //   exactly the order of the reference's per-pixel loop (diff_fp_for.cu:83) -> bit-identical
 //   sinograms, with no global atomics and one coalesced store per pixel.  Backward: per-face
 //   moments in registers, merged across lanes by a segmented shuffle scan, nine RED per (tile, face).
+//   Variants (template parameters of k_raster): EXACT_DIV (literal fp64 divide, debug), DIRECT
+//   (fine meshes: batches of small boxes are walked face-per-lane), STATS (counters compiled in
+//   only when the caller passes a stats buffer).
 #pragma once
 #include "ctdr_common.cuh"
 

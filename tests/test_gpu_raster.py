@@ -253,3 +253,32 @@ def test_fine_mesh_variant_direct_walk(cuda_lib, monkeypatch, name, max_box):
     got = R.raster_backward(g, dev(ref["im"]), *args, c["msv"])
     for a, b in zip(got, base):
         assert (a - b).norm().item() <= 2e-5 * b.norm().item() + 1e-30
+
+
+def _nonfinite_case():
+    """A few faces with NaN / Inf coordinates among ordinary ones: torch.min/max propagate NaN into the
+    reference's bounding box (rasterizer.py:24-25), every comparison with NaN is false (so such a face is
+    neither rejected nor bounded along that axis) and NaN weights pass the inside test (diff_fp_for.cu:149-151)."""
+    c = cases.soup_case(11, B=2, F=300, H=48, W=56, reference_safe=True)
+    p = c["p6"]
+    p[0, 5, 0] = np.nan          # NaN x of vertex a
+    p[0, 17, 3] = np.nan         # NaN y of vertex b
+    p[1, 40, 4] = np.inf         # +Inf x of vertex c: bbox edge off the detector -> whole face rejected
+    p[1, 41, 1] = -np.inf
+    p[1, 99, :] = np.nan         # everything NaN
+    c["len3"][0, 7, 1] = np.nan  # NaN length on an ordinary face
+    return c
+
+
+def test_nonfinite_coordinates_follow_the_reference(cuda_lib):
+    c = _nonfinite_case()
+    ref = oracle.rasterizer_forward(c["p6"], c["len3"], c["ff"], c["labels"], c["mus"], c["H"], c["W"], c["msv"],
+                                    False, fast=True)
+    lit = oracle.rasterizer_forward(c["p6"], c["len3"], c["ff"], c["labels"], c["mus"], c["H"], c["W"], c["msv"],
+                                    False, fast=False)                # the literal pixel-parallel restatement
+    assert np.array_equal(ref["cnt"], lit["cnt"])
+    im, cnt, stats = run_forward(c)
+    assert np.array_equal(cnt, ref["cnt"])
+    nan_ref, nan_got = np.isnan(ref["im"]), np.isnan(im)
+    assert np.array_equal(nan_ref, nan_got) and nan_ref.any()
+    assert np.array_equal(bits(im)[~nan_ref], bits(ref["im"])[~nan_ref])
