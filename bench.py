@@ -348,7 +348,7 @@ def main():
         dist.destroy_process_group()
 
 
-LAUNCHES_PER_STEP = 6   # per angle window: vertex transform, face assemble (+ face and chunk boxes), super-region lists, raster forward, raster residual/backward, vertex backward
+LAUNCHES_PER_STEP = 7   # per angle window: vertex transform, face assemble (+ face and chunk boxes), super-region lists, raster forward (records batches), raster residual/backward replay, its fallback twin, vertex backward
 
 
 def optimise_iteration(torch, niter):

@@ -101,8 +101,15 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
     return 0;
 }
 
+template <int MODE, bool DIRECT, bool LINKED>
+void launch_raster_variant(const RasterParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    if (P.stats) k_raster<MODE, false, DIRECT, true, LINKED><<<blocks, THREADS, smem, st>>>(P);
+    else k_raster<MODE, false, DIRECT, false, LINKED><<<blocks, THREADS, smem, st>>>(P);
+}
+
+// linked: MODE_FWD records its face batches, MODE_STEP is the replay-only kernel (see k_raster)
 template <int MODE>
-int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
+int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool linked = false) {
     const long long blocks = (long long)P.B * P.regions_x * P.regions_y;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*regions too large for one launch");
     // dynamic shared memory: the CTA's grad_mus accumulators, or (MODE_MULTI) the per-warp normal-equation
@@ -113,17 +120,20 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st) {
     const size_t smem = (MODE == MODE_MULTI)
         ? gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
         : raster_smem_bytes(P.n_mus);
-    const bool stats = P.stats != nullptr;
-    if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate
+    constexpr bool SWEEP = (MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP);
+    constexpr bool LINKABLE = (MODE == MODE_FWD || MODE == MODE_STEP);
+    constexpr int MS = SWEEP ? MODE : MODE_FWD, ML = LINKABLE ? MODE : MODE_FWD;   // keep unused branches instantiable
+    // fine meshes (about a pixel per face): batches of small boxes are walked face-per-lane (DIRECT)
+    const bool direct = SWEEP && P.direct_max_box > 0;
+    if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate (never linked)
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-    } else if ((MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP) && P.direct_max_box > 0) {
-        // fine meshes (about a pixel per face): batches of small boxes are walked face-per-lane
-        constexpr int M = (MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP) ? MODE : MODE_FWD;
-        if (stats) k_raster<M, false, true, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-        else k_raster<M, false, true, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+    } else if (linked && LINKABLE) {
+        if (direct) launch_raster_variant<ML, true, true>(P, (unsigned)blocks, smem, st);
+        else launch_raster_variant<ML, false, true>(P, (unsigned)blocks, smem, st);
+    } else if (direct) {
+        launch_raster_variant<MS, true, false>(P, (unsigned)blocks, smem, st);
     } else {
-        if (stats) k_raster<MODE, false, false, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-        else k_raster<MODE, false, false, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        launch_raster_variant<MODE, false, false>(P, (unsigned)blocks, smem, st);
     }
     CTDR_CUDA(cudaGetLastError(), "k_raster launch");
     return 0;
@@ -390,21 +400,36 @@ struct ProjectWs {
     float4* vt;          // [window, V] per-vertex transform records
     float* fs;           // [window, F] per-face attenuation terms (deterministic backward)
     double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
+    // batch records of the residual step (forward sweep records, residual/backward sweep replays)
+    int* brec; int* bhead; int* btail; unsigned char* bflag; int* bcursor; int bcap;
     RasterWs rws;
     int window;   // angles per window
 };
 
 constexpr int DET_LOSS_BLOCKS = 1024;
 
-size_t project_per_angle_bytes(int V, int F, bool bwd) {
+// batch-record capacity per angle: one record per 32 (face, tile) pairs plus one partly filled record per
+// non-empty tile; sized for faces that touch about two tiles (larger ones fall back to the walk, region by region)
+size_t batch_records_per_angle(int F, int H, int W) {
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    return (size_t)F / 16 + tiles / 2 + 64;
+}
+
+size_t batch_record_bytes_per_angle(int F, int H, int W) {
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    const size_t regions2 = (size_t)((W + 2 * TILE - 1) / (2 * TILE)) * ((H + 2 * TILE - 1) / (2 * TILE));   // smallest regions
+    return batch_records_per_angle(F, H, W) * BREC_INTS * sizeof(int) + 2 * tiles * sizeof(int) + regions2 + sizeof(int);
+}
+
+size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+    return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
            MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 18 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
-    const size_t per = project_per_angle_bytes(V, F, bwd);
+    const size_t slack = 26 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    const size_t per = project_per_angle_bytes(V, F, bwd, H, W);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
     if (win > B) win = B;
@@ -424,6 +449,16 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
         ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
         ws->fs = reinterpret_cast<float*>(p + off);    off += align_up((size_t)win * F * 4, 256);
         ws->partials = reinterpret_cast<double*>(p + off); off += align_up(2 * DET_LOSS_BLOCKS * sizeof(double), 256);
+        const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+        const size_t regions2 = (size_t)((W + 2 * TILE - 1) / (2 * TILE)) * ((H + 2 * TILE - 1) / (2 * TILE));
+        size_t cap_a = batch_records_per_angle(F, H, W);          // records per angle; win * cap_a must index as int
+        if (cap_a * (size_t)win > 0x7fffffffULL) cap_a = 0x7fffffffULL / (size_t)win;
+        ws->bcap = (int)cap_a;
+        ws->brec = reinterpret_cast<int*>(p + off);    off += align_up(cap_a * (size_t)win * BREC_INTS * sizeof(int), 256);
+        ws->bhead = reinterpret_cast<int*>(p + off);   off += align_up((size_t)win * tiles * sizeof(int), 256);
+        ws->btail = reinterpret_cast<int*>(p + off);   off += align_up((size_t)win * tiles * sizeof(int), 256);
+        ws->bflag = reinterpret_cast<unsigned char*>(p + off); off += align_up((size_t)win * regions2, 256);
+        ws->bcursor = reinterpret_cast<int*>(p + off); off += align_up((size_t)win * sizeof(int), 256);
     }
     raster_ws_layout((int)win, F, H, W, false, false, &ws->rws, p + off);
     return 0;
@@ -622,14 +657,13 @@ int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles, const in
 }
 
 size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_backward) {
-    (void)H; (void)W;
     if (B <= 0 || F <= 0 || V <= 0) return 0;
-    const size_t per = project_per_angle_bytes(V, F, need_backward != 0);
+    const size_t per = project_per_angle_bytes(V, F, need_backward != 0, H, W);
     const size_t budget = (size_t)8 << 30;               // default window budget: 8 GiB
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 18 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    return per * (size_t)win + 26 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -785,7 +819,14 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         P.im = phat + (size_t)b0 * hw;
-        if (int rc = launch_raster<MODE_FWD>(P, flags, stream)) return rc;
+        if (!det) {             // the forward sweep records its face batches for the residual/backward sweep
+            P.bmode = 1; P.brec = ws.brec; P.bhead = ws.bhead; P.btail = ws.btail; P.bflag = ws.bflag; P.bcursor = ws.bcursor; P.bcap = ws.bcap;
+            if (getenv("CTDR_NO_BATCH_RECORDS") || (flags & CTDR_FLAG_NO_PREFILTER)) P.bmode = 0;   // tuning/debug: no linking
+            if (P.bmode) CTDR_CUDA(cudaMemsetAsync(ws.bcursor, 0, (size_t)nb * sizeof(int), stream), "memset record cursors");
+        }
+        const bool linked = P.bmode == 1;
+        if (int rc = launch_raster<MODE_FWD>(P, flags, stream, linked)) return rc;
+        if (linked) P.bmode = 2;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
         CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
         P.im = nullptr;
@@ -799,6 +840,8 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
             if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, true, flags, stream)) return rc;
             continue;
         }
+        // linked sweeps: the replay-only kernel takes the recorded regions, the ordinary one the rest
+        if (linked) { if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc; }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
         if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
     }

@@ -32,6 +32,7 @@ namespace ctdr {
 
 enum RasterMode { MODE_FWD = 0, MODE_FRAG = 1, MODE_BWD = 2, MODE_STEP = 3, MODE_MULTI = 4 };
 constexpr int MAX_OUT = 4;       // sinograms per MODE_MULTI pass
+constexpr int BREC_INTS = 34;    // ints per batch record
 
 struct RasterParams {
     // inputs at the Rasterizer boundary (rasterizer.py:13)
@@ -77,6 +78,15 @@ struct RasterParams {
     long long out_stride;   // elements between consecutive output sinograms
     double* gram;           // [n_out*n_out + n_out]: sum p_i*p_j (i <= j) and sum p_i*target, or null
     unsigned long long* stats;  // may be null
+    // batch records: the forward sweep of the residual step writes, per tile, the chain of face batches it
+    // processed; the residual/backward sweep replays them instead of rebuilding region lists and queues
+    int    bmode;           // 0 off, 1 record (MODE_FWD), 2 replay (MODE_STEP)
+    int*   brec;            // [B][bcap][BREC_INTS]: {next record or -1, face count, 32 face ids}
+    int*   bhead;           // [B, tiles]: first record of the tile, -1 when no face reached it
+    int*   btail;           // [B, tiles]: last record so far (only regions whose list takes several segments)
+    unsigned char* bflag;   // [B, regions]: 0 = not recorded (fall back to the walk), 1 = recorded, 2 = empty region
+    int*   bcursor;         // [B] next free record of each angle's slice
+    int    bcap;            // records per angle
     int region_major;       // CTA order, see k_raster
     int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
 };
@@ -184,6 +194,7 @@ struct CtaSmem {
     int    wsum[WARPS];
     int    list_n;
     int    next_tile;
+    int    rec_fail;              // batch recording ran out of record space somewhere in this region
     WarpSmem warp[WARPS];
     // the dynamic shared memory holds float gmus[n_mus] (backward modes) or the MODE_MULTI extras
 };
@@ -563,6 +574,24 @@ __device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int 
         }
         if (have) { S.acc[pix] = acc; S.f.hitm[pix] = 0u; }
     }
+}
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register holds the value while it is in flight
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Replay of recorded batches (residual/backward sweep): the next record is fetched into a landing zone in
+// the part of the forward/backward union the backward does not use (behind the three moment rows), while
+// the current batch is being processed.
+__device__ __forceinline__ int* record_landing(WarpSmem& S) { return reinterpret_cast<int*>(S.f.hitm + 128); }
+__device__ __forceinline__ void prefetch_record(const RasterParams& P, WarpSmem& S, int off, int lane) {
+    const int* r = P.brec + (long long)off * BREC_INTS;
+    int* L = record_landing(S);
+    cp_async4(L + 2 + lane, r + 2 + lane);
+    if (lane < 2) cp_async4(L + lane, r + lane);
 }
 
 // MODE_MULTI dynamic shared memory after CtaSmem: per-warp normal-equation sums (NGRAM doubles each),
@@ -1096,9 +1125,15 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
 // ------------------------------------------------------------------------------------------
 // the raster kernel: one CTA per (angle, region)
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true>
+// LINKED: the two sweeps of the residual step are linked by batch records.  MODE_FWD + LINKED records the face
+// batches of every tile; MODE_STEP + LINKED is a replay-only kernel (no region lists, no queues) that skips
+// the regions the forward sweep could not record — those are done by the ordinary MODE_STEP kernel, launched
+// right after it with bmode == 2, which in turn skips the recorded ones.
+template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
+    constexpr bool RECORD = LINKED && MODE == MODE_FWD;
+    constexpr bool REPLAY = LINKED && MODE == MODE_STEP;
     // fixed-size state in STATIC shared memory (addresses are link-time constants: no base pointer to keep
     // or rebuild in the hot loops); the dynamic part holds grad_mus accumulators / MODE_MULTI extras
     __shared__ CtaSmem C;
@@ -1136,6 +1171,16 @@ k_raster(const RasterParams P) {
 
     int c = 0;
     int seg = 0;
+    // residual/backward sweep: what the forward sweep recorded for this region (0: nothing, walk as usual)
+    int bflag = 0;
+    if (MODE == MODE_STEP && (REPLAY || P.bmode == 2)) {
+        bflag = (int)P.bflag[(long long)b * regions + rr];
+        if (REPLAY ? bflag == 0 : bflag != 0) return;         // the other kernel of the pair owns this region
+    }
+    constexpr bool replay = REPLAY;
+    const int tiles_x = (P.W + TILE - 1) / TILE, tiles_y = (P.H + TILE - 1) / TILE;
+    if (RECORD && tid == 0) C.rec_fail = 0;
+    if (REPLAY) c = nsuper;                                   // no region list needed
     do {
         // ---- phase A: ordered compaction of the chunks overlapping this region -------------
         if (tid == 0) { C.list_n = 0; C.next_tile = 0; }
@@ -1172,7 +1217,9 @@ k_raster(const RasterParams P) {
         const int nlist = C.list_n;
         const bool first = (seg == 0), last = (c >= nsuper);
 
-        if (nlist == 0 && first && last) {
+        constexpr bool recording = RECORD;
+        if (nlist == 0 && first && last && !(REPLAY && bflag == 1)) {
+            if (RECORD && tid == 0) P.bflag[(long long)b * regions + rr] = 2;
             // nothing projects into this region: zero-fill (forward); the residual step still owes
             // the data term of its (all-zero, hence valid) pixels; nothing to do otherwise
             const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
@@ -1233,6 +1280,20 @@ k_raster(const RasterParams P) {
             const int tx0 = rx0 + (int)tcol * TILE, ty0 = ry0 + (int)trow * TILE;
             if (tx0 > rx1 || ty0 > ry1) continue;
             const int tx1 = min(tx0 + TILE - 1, rx1), ty1 = min(ty0 + TILE - 1, ry1);
+            // batch records of this tile: replaying, `roff` is the next record; recording, the previous one
+            const long long head_index = ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4);
+            int roff = -1;
+            if (replay) {
+                roff = __ldg(P.bhead + head_index);
+                if (roff >= 0) prefetch_record(P, S, roff, lane);      // in flight during the tile prologue
+            }
+            // recording across list segments: the tile's chain continues from the tail the previous segment
+            // left (plain loads: written by another warp of this CTA before the last barrier)
+            bool head_unset = true;
+            if (recording && !first) {
+                roff = *reinterpret_cast<volatile int*>(P.btail + head_index);
+                head_unset = roff < 0;
+            }
 
             // tile prologue
             if (MODE == MODE_FWD) {
@@ -1316,7 +1377,24 @@ k_raster(const RasterParams P) {
             unsigned m = 0u;
             bool exhausted = false;
             const short4* fbrow = P.face_box + (long long)b * P.F;
+            int rfirst = -1;
             while (true) {
+                int nbatch;
+                if (replay) {
+                    // the forward sweep already found this tile's faces and cut them into batches
+                    if (roff < 0) break;
+                    cp_async_wait_all();
+                    __syncwarp();
+                    const int* L = record_landing(S);
+                    nbatch = L[1];
+                    const int next = L[0];
+                    const int id = L[2 + lane];
+                    __syncwarp();                               // the landing zone may be overwritten now
+                    if (lane < nbatch) S.qface[lane] = id;
+                    roff = next;
+                    if (roff >= 0) prefetch_record(P, S, roff, lane);   // lands while this batch is processed
+                    __syncwarp();
+                } else {
                 while (qn < 32 && !exhausted) {
                     if (m == 0u) {
                         if (lb >= nlist) { exhausted = true; break; }
@@ -1356,20 +1434,47 @@ k_raster(const RasterParams P) {
                     __syncwarp();
                 }
                 if (qn == 0) break;
-                const int nbatch = min(qn, 32);
+                nbatch = min(qn, 32);
+                if (recording) {
+                    // one cursor and one slice of bcap records per angle: concurrent CTAs (region-major order:
+                    // same region, different angles) hit different counters
+                    int off = 0;
+                    if (lane == 0) off = atomicAdd(P.bcursor + b, 1);
+                    off = __shfl_sync(FULL, off, 0);
+                    if (off < P.bcap) {
+                        off += b * P.bcap;
+                        int* r = P.brec + (long long)off * BREC_INTS;
+                        if (lane < nbatch) r[2 + lane] = S.qface[lane];
+                        if (lane == 0) {
+                            r[0] = -1; r[1] = nbatch;
+                            if (roff >= 0) P.brec[(long long)roff * BREC_INTS] = off;
+                        }
+                        if (rfirst < 0) rfirst = off;
+                        roff = off;
+                    } else if (lane == 0) {
+                        C.rec_fail = 1;
+                    }
+                }
+                }
                 if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
                 else process_batch_blocked<MODE, EXACT_DIV, DIRECT>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
-                const int rest = qn - nbatch;                  // < 32: shift the tail to the front
-                int tf = 0;
-                if (lane < rest) tf = S.qface[32 + lane];
-                __syncwarp();
-                if (lane < rest) S.qface[lane] = tf;
-                qn = rest;
-                __syncwarp();
+                if (!replay) {
+                    const int rest = qn - nbatch;              // < 32: shift the tail to the front
+                    int tf = 0;
+                    if (lane < rest) tf = S.qface[32 + lane];
+                    __syncwarp();
+                    if (lane < rest) S.qface[lane] = tf;
+                    qn = rest;
+                    __syncwarp();
+                }
             }
 
             // tile epilogue
             if (MODE == MODE_FWD) {
+                if (recording && lane == 0) {
+                    if (head_unset) P.bhead[head_index] = rfirst;
+                    if (!last) P.btail[head_index] = roff;
+                }
                 tile_store<float>(P.im, S.acc, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
                 if (P.cnt) tile_store<int>(P.cnt, S.cntv, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
             } else if (MODE == MODE_MULTI) {
@@ -1423,6 +1528,10 @@ k_raster(const RasterParams P) {
         __syncthreads();
         ++seg;
     } while (c < nsuper);
+    // forward sweep with recording: the region is replayable when every batch found record space
+    // (seg == 0: empty region, flagged above)
+    if (RECORD && tid == 0 && seg > 0)
+        P.bflag[(long long)b * regions + rr] = (C.rec_fail == 0) ? 1 : 0;
 
     if (K_BWD) {
         st.mus_flush(gmus);
