@@ -61,8 +61,9 @@ def main(rep, lib, src_path):
                 name = n
         return name
 
-    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0", "k_rasterILi0ELb0ELb0ELb0"),
-                           ("k_raster<(int)3, (bool)0, (bool)0, (bool)0", "k_rasterILi3ELb0ELb0ELb0")):
+    # the two kernels of the residual step: forward (records batches) and the replay-only residual/backward
+    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1", "k_rasterILi0ELb0ELb0ELb0ELb1"),
+                           ("k_raster<(int)3, (bool)0, (bool)0, (bool)0, (bool)1", "k_rasterILi3ELb0ELb0ELb0ELb1")):
         try:
             blk = S.ncu_rows(rep, ksub_ncu)
         except SystemExit:
