@@ -57,7 +57,7 @@ int pick_region_tiles(int B, int F, int H, int W) {
     // region lists are long (very fine meshes: fewer list segments).  Measured on config 3 / north star.
     int rt = 8;
     const long long regions8 = (long long)((W + 8 * TILE - 1) / (8 * TILE)) * ((H + 8 * TILE - 1) / (8 * TILE));
-    if (regions8 * B < 128LL * 148 || F > 300000) rt = 4;
+    if (regions8 * B < 88LL * 148 || F > 300000) rt = 4;      // config 3: 4x4 wins up to 180 angles per GPU, 8x8 from 240
     const long long regions4 = (long long)((W + 4 * TILE - 1) / (4 * TILE)) * ((H + 4 * TILE - 1) / (4 * TILE));
     if (regions4 * B < 2LL * 148) rt = 2;
     return rt;
