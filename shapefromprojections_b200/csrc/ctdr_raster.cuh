@@ -1281,18 +1281,19 @@ k_raster(const RasterParams P) {
             if (tx0 > rx1 || ty0 > ry1) continue;
             const int tx1 = min(tx0 + TILE - 1, rx1), ty1 = min(ty0 + TILE - 1, ry1);
             // batch records of this tile: replaying, `roff` is the next record; recording, the previous one
-            const long long head_index = ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4);
+            // (the index is recomputed where needed instead of being held across the batch loop)
+#define CTDR_HEAD_INDEX (((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4))
             int roff = -1;
             if (replay) {
-                roff = __ldg(P.bhead + head_index);
+                roff = __ldg(P.bhead + CTDR_HEAD_INDEX);
                 if (roff >= 0) prefetch_record(P, S, roff, lane);      // in flight during the tile prologue
             }
-            // recording across list segments: the tile's chain continues from the tail the previous segment
-            // left (plain loads: written by another warp of this CTA before the last barrier)
-            bool head_unset = true;
-            if (recording && !first) {
-                roff = *reinterpret_cast<volatile int*>(P.btail + head_index);
-                head_unset = roff < 0;
+            if (recording) {
+                // first segment: no chain yet (the head is overwritten by the first record); later segments
+                // continue from the tail the previous one left (plain load: written by another warp of this
+                // CTA before the last barrier)
+                if (first) { if (lane == 0) P.bhead[CTDR_HEAD_INDEX] = -1; }
+                else roff = *reinterpret_cast<volatile int*>(P.btail + CTDR_HEAD_INDEX);
             }
 
             // tile prologue
@@ -1377,7 +1378,6 @@ k_raster(const RasterParams P) {
             unsigned m = 0u;
             bool exhausted = false;
             const short4* fbrow = P.face_box + (long long)b * P.F;
-            int rfirst = -1;
             while (true) {
                 int nbatch;
                 if (replay) {
@@ -1447,9 +1447,9 @@ k_raster(const RasterParams P) {
                         if (lane < nbatch) r[2 + lane] = S.qface[lane];
                         if (lane == 0) {
                             r[0] = -1; r[1] = nbatch;
-                            if (roff >= 0) P.brec[(long long)roff * BREC_INTS] = off;
+                            if (roff >= 0) P.brec[(long long)roff * BREC_INTS] = off;     // link behind the previous record
+                            else P.bhead[CTDR_HEAD_INDEX] = off;                          // first record of the tile
                         }
-                        if (rfirst < 0) rfirst = off;
                         roff = off;
                     } else if (lane == 0) {
                         C.rec_fail = 1;
@@ -1471,10 +1471,7 @@ k_raster(const RasterParams P) {
 
             // tile epilogue
             if (MODE == MODE_FWD) {
-                if (recording && lane == 0) {
-                    if (head_unset) P.bhead[head_index] = rfirst;
-                    if (!last) P.btail[head_index] = roff;
-                }
+                if (recording && !last && lane == 0) P.btail[CTDR_HEAD_INDEX] = roff;
                 tile_store<float>(P.im, S.acc, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
                 if (P.cnt) tile_store<int>(P.cnt, S.cntv, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
             } else if (MODE == MODE_MULTI) {
@@ -1525,6 +1522,7 @@ k_raster(const RasterParams P) {
             }
             __syncwarp();
         }
+#undef CTDR_HEAD_INDEX
         __syncthreads();
         ++seg;
     } while (c < nsuper);
