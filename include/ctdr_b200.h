@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CTDR_ABI_VERSION 1
+#define CTDR_ABI_VERSION 2   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi */
 
 /* argument errors */
 #define CTDR_E_NULL      (-1)   /* a required pointer is NULL */
@@ -226,7 +226,10 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles,
  * max_sino_val - 1e-6; loss_sum = sum_valid (target - phat)^2, n_valid = #valid; the UNNORMALISED
  * gradient of loss_sum is accumulated into grad_verts / grad_mus (divide by n_valid — after the
  * cross-GPU all-reduce — to get d(mean)/d·).  out2 = device float64[2] {loss_sum, n_valid}
- * (accumulated; arrives zeroed).  phat [B,H,W] is written (needed by the reference's logging). */
+ * (accumulated; arrives zeroed).  phat [B,H,W] is written (needed by the reference's logging).
+ * The forward sweep records the face batches of every tile in the workspace and the residual/backward
+ * sweep replays them (no second binning); the workspace must come from
+ * ctdr_project_workspace_bytes(..., need_backward = 1). */
 int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles,
                                const int64_t* idx_angles, int B,
                                const float* verts, int V, const int32_t* faces, int F,

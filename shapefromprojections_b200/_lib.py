@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libctdr_b200.so")
 
 FLAG_NO_PREFILTER = 1
 FLAG_DETERMINISTIC = 2
+ABI_VERSION = 2          # include/ctdr_b200.h: CTDR_ABI_VERSION
 STAT_NONPOSITIVE_LEN, STAT_FRAGMENTS, STAT_CANDIDATES, STAT_LIST_SEGMENTS, STAT_COUNT = 0, 1, 2, 3, 8
 GEOM_PARALLEL3D, GEOM_PARALLEL3D_VEC, GEOM_CONE_VEC = 0, 1, 2
 GEOM_KINDS = {"parallel3d": GEOM_PARALLEL3D, "parallel3d_vec": GEOM_PARALLEL3D_VEC, "cone_vec": GEOM_CONE_VEC}
@@ -61,7 +62,7 @@ def lib() -> ctypes.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.ctdr_abi_version() != 1:
+        if handle.ctdr_abi_version() != ABI_VERSION:
             raise RuntimeError("libctdr_b200.so: unexpected ABI version")
         _lib = handle
     return _lib

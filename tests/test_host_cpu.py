@@ -27,7 +27,7 @@ def test_shared_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), name
     handle.ctdr_abi_version.restype = ctypes.c_int
-    assert handle.ctdr_abi_version() == 1
+    assert handle.ctdr_abi_version() == 2
     # argument validation happens before any CUDA call: usable without a device
     _lib.lib()
     rc = _lib.lib().ctdr_raster_forward(None, None, None, None, None, 1, 1, 1, 8, 8, 1.0, None, None, None, 0, None, 0, None)
