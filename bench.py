@@ -320,21 +320,31 @@ def main():
     if breakdown is not None:
         line["kernels"] = breakdown
         if "raster_step_ms" in breakdown:
-            k_bytes = 8 * Bl * H * W      # the kernel's own algorithmic bytes: 4 B phat + 4 B target/gradient per pixel
-            traffic = None
+            # the two raster sweeps are the step's dominant kernels (42 % / 39 % of it in the ncu launch list);
+            # both are timed live here through the staged C-ABI entry points (same kernels, unlinked: inside the
+            # fused step the forward also records its face batches, +5 %, and the residual/backward sweep replays
+            # them instead of walking its own lists, -25 %)
+            tj = None
             tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
             if os.path.exists(tpath):
                 with open(tpath) as fh:
                     tj = json.load(fh).get(args.config)
-                if tj and tj.get("angles") == Bl:
-                    traffic = tj.get("k_raster<MODE_STEP>")
-            line["roofline"]["traffic"] = traffic
-            line["roofline"]["dominant_kernel"] = {
-                "name": "k_raster<MODE_STEP> (residual + backward sweep; timed as the staged MODE_BWD launch, same traversal)",
-                "ms": breakdown["raster_step_ms"], "algorithmic_bytes": k_bytes,
-                "achieved": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9, "unit": "GB/s",
-                "frac": k_bytes / (breakdown["raster_step_ms"] / 1e3) / 1e9 / peak,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1_ncu_cfg3_summary.md)"}
+                if not (tj and tj.get("angles") == Bl):
+                    tj = None
+
+            def kernel_roofline(name, ms, nbytes, key):
+                return {"name": name, "ms": ms, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
+                        "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": tj.get(key) if tj else None,
+                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                          "(profiles/r1_ncu_cfg3_summary.md)"}
+            fwd = kernel_roofline("k_raster<MODE_FWD> (forward sweep: 4 B sinogram store per pixel)",
+                                  breakdown["raster_forward_ms"], 4 * Bl * H * W, "k_raster<MODE_FWD>")
+            bwd = kernel_roofline("k_raster residual + backward sweep (4 B phat + 4 B target per pixel; timed as the staged "
+                                  "MODE_BWD launch, same traversal)", breakdown["raster_step_ms"], 8 * Bl * H * W,
+                                  "k_raster<MODE_STEP>")
+            line["roofline"]["dominant_kernel"] = fwd
+            line["roofline"]["second_kernel"] = bwd
+            line["roofline"]["traffic"] = fwd["traffic"]
     if not args.no_optimise and world == 1:
         import contextlib
         with contextlib.redirect_stdout(sys.stderr):       # the reference-style modules print; stdout carries the JSON line only
