@@ -26,6 +26,10 @@ def test_shared_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
+    # the ctypes signatures carry as many arguments as the header declares for each entry point
+    for name, params in re.findall(r"\b(ctdr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S):
+        n = 0 if params.strip() in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
     handle.ctdr_abi_version.restype = ctypes.c_int
     assert handle.ctdr_abi_version() == 2
     # argument validation happens before any CUDA call: usable without a device
