@@ -159,3 +159,18 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_normal_equation_layout_helper():
+    """The multi-output pass returns the upper triangle of the Gram matrix and the right-hand side in one
+    flat float64 buffer (include/ctdr_b200.h); the binding mirrors it into a symmetric matrix."""
+    from shapefromprojections_b200.function.rasterizer import _gram_matrices
+    K = 3
+    flat = torch.zeros(K * K + K, dtype=torch.float64)
+    full = torch.tensor([[4.0, 1.0, 2.0], [1.0, 5.0, 3.0], [2.0, 3.0, 6.0]], dtype=torch.float64)
+    for i in range(K):
+        for j in range(i, K):
+            flat[i * K + j] = full[i, j]           # the kernel leaves the lower triangle at zero
+    flat[K * K:] = torch.tensor([7.0, 8.0, 9.0], dtype=torch.float64)
+    A, rhs = _gram_matrices(flat, K)
+    assert torch.equal(A, full) and torch.equal(rhs, flat[K * K:])
