@@ -28,7 +28,9 @@ def available() -> bool:
 def forward(p6, len3, ff, labels, mus, H, W, msv, dtype=torch.float32):
     """Returns dict of CUDA tensors: im, cnt, firstidx, imidx, imwei, bbox (+ inputs)."""
     m = module()
-    t = lambda a, d=dtype: torch.as_tensor(np.ascontiguousarray(a)).to(d).cuda().contiguous()
+    def t(a, d=dtype):      # NumPy arrays or tensors (already on the device: no round trip through the host)
+        a = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+        return a.to(d).cuda().contiguous()
     p6, len3, ff, mus = t(p6), t(len3), t(ff), t(mus)
     labels = t(labels, torch.int32)
     B, F = p6.shape[:2]
@@ -54,7 +56,8 @@ def forward(p6, len3, ff, labels, mus, H, W, msv, dtype=torch.float32):
 
 def backward(fwd, grad_im):
     m = module()
-    g = torch.as_tensor(np.ascontiguousarray(grad_im)).to(fwd["im"].dtype).cuda().contiguous()
+    g = grad_im if torch.is_tensor(grad_im) else torch.as_tensor(np.ascontiguousarray(grad_im))
+    g = g.to(fwd["im"].dtype).cuda().contiguous()
     dldp = torch.zeros_like(fwd["p6"]); dldf = torch.zeros_like(fwd["len3"]); dldmu = torch.zeros_like(fwd["mus"])
     m.backward(g, fwd["im"], fwd["imidx"], fwd["cnt"], fwd["firstidx"], fwd["imwei"], fwd["p6"], fwd["len3"],
                fwd["labels"], fwd["mus"], fwd["ff"], dldp, dldf, dldmu)               # :101-105

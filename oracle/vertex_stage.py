@@ -10,8 +10,13 @@ NumPy restatement (op by op, in the working dtype) of the reference's per-angle 
 Outputs are exactly the three tensors the reference hands to ``Rasterizer.apply``:
 ``p_bxfx6``, ``len_bxfx3``, ``front_facing_bxfx1`` and ``max_sino_val``.
 
+``vertex_stage_vjp`` is the hand-written reverse mode of the same chains (what torch autograd does through
+the reference modules: index_backward scatter-adds of the gathers at fp_opengl.py:126-135 /
+fp_vecs.py:176-186, then the transposed per-vertex transform), in float64.
+
 Parity pin: ``tests/golden/vertex_stage_*.npz`` were produced by importing the reference's own
-``FP`` modules in the build container with ``.cuda()`` stubbed (``tests/golden/make_vertex_golden.py``).
+``FP`` modules in the build container with ``.cuda()`` stubbed (``tests/golden/make_vertex_golden.py``);
+they hold the forward tensors and ``grad_verts`` from the reference's autograd for seeded cotangents.
 """
 from __future__ import annotations
 
@@ -157,3 +162,82 @@ def vertex_stage(proj_geom, verts, faces, idx_angles, dtype=np.float32):
     if proj_geom["type"][-3:] == "vec":
         return vertex_stage_vecs(proj_geom, verts, faces, idx_angles, dtype)
     return vertex_stage_opengl(proj_geom, verts, faces, idx_angles, dtype)
+
+
+# ----------------------------------------------------------------------------- reverse mode
+def _scatter_corners(faces, gp6, glen3, V):
+    """index_backward of the per-face gathers: [B,F,6]/[B,F,3] -> per-vertex (gpx, gpy, glen) [B,V]."""
+    f = np.asarray(faces)
+    B = gp6.shape[0]
+    gpx, gpy, gl = (np.zeros((B, V)) for _ in range(3))
+    for k in range(3):
+        for b in range(B):
+            np.add.at(gpx[b], f[:, k], gp6[b, :, 2 * k])
+            np.add.at(gpy[b], f[:, k], gp6[b, :, 2 * k + 1])
+            np.add.at(gl[b], f[:, k], glen3[b, :, k])
+    return gpx, gpy, gl
+
+
+def vertex_stage_vjp(proj_geom, verts, faces, idx_angles, gp6, glen3):
+    """grad_verts [V,3] (float64) = J^T (gp6, glen3) of ``vertex_stage`` (front_facing carries no
+    gradient, rasterizer.py:107), summed over the angles in ``idx_angles``."""
+    d = np.float64
+    v = np.asarray(verts, dtype=d)
+    V = v.shape[0]
+    gp6, glen3 = np.asarray(gp6, dtype=d), np.asarray(glen3, dtype=d)
+    gpx, gpy, gl = _scatter_corners(faces, gp6, glen3, V)
+    W, H = proj_geom["DetectorColCount"], proj_geom["DetectorRowCount"]
+    idx = np.asarray(idx_angles)
+    x, y, z = v[None, :, 0], v[None, :, 1], v[None, :, 2]
+    if proj_geom["type"][-3:] != "vec":                              # fp_opengl.py:87-158 reversed
+        msv = W * proj_geom["DetectorSpacingX"] * 2
+        P = ortho_P(proj_geom).astype(d)
+        th = np.asarray(proj_geom["ProjectionAngles"]).astype(d)[idx]
+        ct, st = np.cos(th)[:, None], np.sin(th)[:, None]
+        xr, yr = x * ct + y * st, -x * st + y * ct
+        cam = np.stack([xr, np.broadcast_to(-z, xr.shape), yr - msv], axis=2)
+        length = np.sqrt((cam * cam).sum(axis=2))
+        g_ndc0 = gpx * (W / 2.0) / (1.0 + 1e-8)                      # :157 then :113
+        g_ndc1 = -gpy * (H / 2.0) / (1.0 + 1e-8)                     # :158 then :113
+        g_cam = gl[..., None] * cam / length[..., None]              # :107
+        g_cam[..., 0] += P[0, 0] * g_ndc0                            # :111
+        g_cam[..., 1] += P[1, 1] * g_ndc1
+        gx = ct * g_cam[..., 0] - st * g_cam[..., 2]                 # :91-92
+        gy = st * g_cam[..., 0] + ct * g_cam[..., 2]
+        gz = -g_cam[..., 1]                                          # M_left: cam y = -z
+        return np.stack([gx.sum(0), gy.sum(0), gz.sum(0)], axis=1)
+    kind = proj_geom["type"]
+    msv = W * proj_geom["DetectorSpacingX"] * (3 if kind == "parallel3d_vec" else 100)
+    vecs_all = np.asarray(proj_geom["Vectors"]).astype(d)
+    det_pos_all = vecs_all[:, 3:6] if kind == "cone_vec" else -msv * vecs_all[:, 0:3]
+    vecs, det_pos = vecs_all[idx], det_pos_all[idx]
+    B = vecs.shape[0]
+    N = np.stack([vecs[:, 7] * vecs[:, 11], -vecs[:, 6] * vecs[:, 11]], axis=1)
+    use_x = np.abs(vecs[:, 6]) > np.abs(vecs[:, 7])
+    gP = np.zeros((B, V, 3))                                         # :171-173 reversed
+    gP[use_x, :, 0] = gpx[use_x] / vecs[use_x, 6][:, None]
+    gP[~use_x, :, 1] = gpx[~use_x] / vecs[~use_x, 7][:, None]
+    gP[:, :, 2] = gpy / vecs[:, 11][:, None]
+    if kind == "parallel3d_vec":
+        N = N / np.sqrt(N[:, 0:1] ** 2 + N[:, 1:2] ** 2)
+        Rn = -vecs[:, None, 0:3]                                     # constant ray
+        NR = (N * Rn[:, 0, :2]).sum(axis=1)[:, None]
+        g_t = (gP * Rn).sum(axis=2) + gl                             # :153, :137
+        g_v = gP.copy()                                              # Pt = v + t*Rn
+        g_v[..., 0] += -g_t * N[:, 0:1] / NR                         # t = -(N.v_xy + msv)/NR
+        g_v[..., 1] += -g_t * N[:, 1:2] / NR
+        return g_v.sum(axis=0)
+    S = vecs[:, None, 0:3]
+    R = np.broadcast_to(v[None], (B, V, 3)) - S
+    length = np.sqrt((R * R).sum(axis=2))
+    Rn = R / length[..., None]
+    coeff = -((N * vecs[:, 0:2]).sum(axis=1) - (N * det_pos[:, 0:2]).sum(axis=1))
+    NRe = (N[:, None, :] * Rn[:, :, :2]).sum(axis=2) + 1e-10
+    t = coeff[:, None] / NRe
+    g_t = (gP * Rn).sum(axis=2)                                      # Pt = S + t*Rn
+    g_Rn = t[..., None] * gP
+    g_NR = -g_t * t / NRe                                            # t = coeff / NRe
+    g_Rn[..., 0] += g_NR * N[:, 0:1]
+    g_Rn[..., 1] += g_NR * N[:, 1:2]
+    g_R = (g_Rn - Rn * (Rn * g_Rn).sum(axis=2, keepdims=True)) / length[..., None] + gl[..., None] * Rn
+    return g_R.sum(axis=0)

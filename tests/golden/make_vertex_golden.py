@@ -8,7 +8,10 @@ The reference's ``ctdr/nn/fp_opengl.py`` / ``ctdr/nn/fp_vecs.py`` are imported u
 ``Tensor.cuda`` / ``Module.cuda`` stubbed to identity (no GPU here) and the native module
 ``cuda_diff_fp`` replaced by an empty stub; ``FP.rasterize`` is swapped for a recorder so what is
 captured is exactly what the reference hands to ``Rasterizer.apply``
-(p_bxfx6, len_bxfx3, front_facing_bxfx1, max_sino_val).  Geometry dicts come from the reference's
+(p_bxfx6, len_bxfx3, front_facing_bxfx1, max_sino_val).  The recorder keeps the autograd graph, so
+``grad_verts`` = the REFERENCE'S OWN autograd through its ~40 torch ops (fp_opengl.py:87-158,
+fp_vecs.py:85-196) for seeded cotangents on p_bxfx6 / len_bxfx3 is stored too (``cotangents(seed, B, F)``
+below regenerates them in the tests): the pin for ctdr_vertex_backward and the fused backward.  Geometry dicts come from the reference's
 ``util_sino.read_from_toml`` / ``geom_2vec`` on the shipped ``data/2starA/proj_geom.toml`` and on
 a cone geometry with the numbers of ``run/simulation_cone_beam.py:22-23``.
 """
@@ -22,8 +25,9 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
-sys.path.insert(0, REPO)
-sys.path.insert(0, REF)
+# the repository carries an alias package `ctdr/` (a regular package: it would shadow the reference's
+# namespace package), so the reference modules are imported with only /root/reference on the path
+sys.path = [REF] + [p for p in sys.path if os.path.abspath(p or ".") != REPO]
 
 sys.modules["cuda_diff_fp"] = types.ModuleType("cuda_diff_fp")     # native module: not needed here
 torch.Tensor.cuda = lambda self, *a, **k: self                       # no GPU in this container
@@ -33,22 +37,39 @@ from ctdr.nn import fp_opengl as ref_opengl                          # noqa: E40
 from ctdr.nn import fp_vecs as ref_vecs                              # noqa: E402
 from ctdr.utils import util_sino as ref_sino                         # noqa: E402
 
+assert ref_vecs.__file__.startswith(REF) and ref_opengl.__file__.startswith(REF)
+sys.path.insert(1, REPO)
 from shapefromprojections_b200.utils import meshgen                  # noqa: E402
+
+
+COT_SEED = 20
+
+
+def cotangents(seed, B, F):
+    """Seeded float32 cotangents on (p_bxfx6, len_bxfx3); the tests call this with the stored seed."""
+    rng = np.random.default_rng(seed)
+    return rng.normal(size=(B, F, 6)).astype(np.float32), rng.normal(size=(B, F, 3)).astype(np.float32)
 
 
 def capture(fp_module, proj_geom, verts, faces, idx, dtype):
     labels = torch.zeros(faces.shape[0], 2, dtype=torch.int32)
     fp = fp_module.FP(proj_geom, labels, dtype)
-    got = {}
+    got, live = {}, {}
 
     def recorder(p6, len3, ff, labels_, mus, H, W, msv, backprop):
         got.update(p6=p6.detach().numpy().copy(), len3=len3.detach().numpy().copy(),
                    ff=ff.detach().numpy().copy(), msv=float(msv), H=H, W=W)
+        live.update(p6=p6, len3=len3)
         return torch.zeros(p6.shape[0], H, W, 1, dtype=dtype)
 
     fp.rasterize = recorder
-    fp.forward(torch.tensor(verts, dtype=dtype), torch.tensor(faces, dtype=torch.int64),
-               torch.tensor(idx, dtype=torch.int64), torch.tensor([0.0, 1.0], dtype=dtype), False)
+    v = torch.tensor(verts, dtype=dtype, requires_grad=True)
+    fp.forward(v, torch.tensor(faces, dtype=torch.int64),
+               torch.tensor(idx, dtype=torch.int64), torch.tensor([0.0, 1.0], dtype=dtype), True)
+    gp6, gl3 = cotangents(COT_SEED, len(idx), faces.shape[0])
+    phi = (live["p6"] * torch.tensor(gp6, dtype=dtype)).sum() + (live["len3"] * torch.tensor(gl3, dtype=dtype)).sum()
+    got["grad_verts"] = torch.autograd.grad(phi, v)[0].numpy().copy()     # the reference's autograd (index_backward scatter-adds ...)
+    got["cot_seed"] = COT_SEED
     return got
 
 
