@@ -3,9 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
 
-One "step" = one projection + masked-L2 residual + backward sweep over ALL angles of the workload
-(angles sharded over the N ranks, mesh replicated) followed by the all-reduce of the gradients —
-the data-path of one optimiser iteration (ctdr/optimize.py:162-190).  Prints ONE JSON line on rank 0.
+Default (--config cfg3, the configuration BASELINE.json's metric is quoted on; also cfg1, cfg4, northstar,
+cfg3_small): one "step" = one projection + masked-L2 residual + backward sweep over ALL angles of the workload
+(angles sharded over the N ranks, mesh replicated) followed by the all-reduce of the gradients — the data path of
+one optimiser iteration (ctdr/optimize.py:162-190).
+--config cfg5: batched simulation, forward only (run/simulation_cone_beam.py:63-82), the 64 meshes sharded over
+the ranks, no collective.  --config cfg2: BASELINE.json's second metric, s per optimise iteration, on the 2bunnyA
+geometry for 500 iterations (one GPU).
+Prints ONE JSON line on rank 0.  Every number is measured where its key says (no aliases): `kernels.*_ms` are the
+stages of the step as they run inside it (CUDA events between the stages, ctdr_project_residual_step_timed),
+`gpu_launches` is the library's own launch counter over the timed region.
 """
 from __future__ import annotations
 
@@ -23,7 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "fwd+bwd detector Gpix/s"
-CPU_SAMPLE = dict(angles=2, rows=32)          # bounded sample of the workload for the CPU arm
+CPU_SAMPLE = dict(angles=2, rows=64)          # bounded sample of the workload for the CPU arm
+STEP_CONFIGS = ("cfg1", "cfg3", "cfg3_small", "cfg4", "northstar")
 
 
 def parse():
@@ -31,12 +39,13 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--config", default="cfg3", choices=list(STEP_CONFIGS) + ["cfg2", "cfg5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-optimise", action="store_true")
+    ap.add_argument("--no-reference-ext", action="store_true")
     ap.add_argument("--optimise-iters", type=int, default=100)
     return ap.parse_args()
 
@@ -49,19 +58,31 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads():
+    """Cores this process may use (affinity mask when the platform has one)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm on the host cores (oracle port; the extension has no CPU path)
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_sample(wl, repeats=1):
     """Time vertex stage + Rasterizer forward (pass 1 + pass 2) + backward of the reference
-    algorithm (pixel-parallel, loop over all faces) on CPU_SAMPLE of the workload."""
+    algorithm (pixel-parallel, loop over all faces) on CPU_SAMPLE of the workload.
+    Returns (Gpix/s, seconds, sample description, OpenMP threads used)."""
     from oracle import oracle, vertex_stage
+    lib = oracle.lib()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: set the count explicitly and report what OpenMP uses
+    lib.oracle_set_threads(host_threads())
+    threads = int(lib.oracle_max_threads())
     na, rows = CPU_SAMPLE["angles"], CPU_SAMPLE["rows"]
     H, W = wl["H"], wl["W"]
     na = min(na, wl["nangles"]); rows = min(rows, H)
     idx = np.linspace(0, wl["nangles"], na, endpoint=False).astype(np.int64)
     y0 = (H - rows) // 2
-    oracle.lib()
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -89,7 +110,8 @@ def cpu_reference_sample(wl, repeats=1):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     pixels = na * rows * W
-    return pixels / best / 1e9, best, f"{na} angles x {rows} detector rows x {W} cols x full mesh ({wl['faces'].shape[0]} faces)"
+    return (pixels / best / 1e9, best,
+            f"{na} angles x {rows} detector rows x {W} cols x full mesh ({wl['faces'].shape[0]} faces)", threads)
 
 
 def run_reference_arm(args):
@@ -97,11 +119,11 @@ def run_reference_arm(args):
     if rank != 0:
         return
     from shapefromprojections_b200 import workloads
-    wl = workloads.make_workload(args.config)
-    cores = os.cpu_count()
-    times = []
+    name = "cfg1" if args.config == "cfg2" else args.config
+    wl = workloads.make_workload(name)
+    times, threads, sample = [], 1, ""
     for i in range(args.warmup + args.steps):
-        gpix, dt, sample = cpu_reference_sample(wl)
+        gpix, dt, sample, threads = cpu_reference_sample(wl)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -111,9 +133,10 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {wl['desc']}",
-                       "sample": f"reference algorithm (oracle port) on the host cores; each step = a bounded sample "
-                                 f"({sample}); pixels are independent in that algorithm, so the sample rate is the full-job rate"},
-            "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": cores, "kind": "port", "sample": sample},
+                       "sample": f"reference algorithm (oracle port, OpenMP, {threads} threads) on the host cores; each step = a "
+                                 f"bounded sample ({sample}); pixels are independent in that algorithm, so the sample rate is the full-job rate"},
+            "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": threads, "kind": "port", "sample": sample,
+                             "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -162,6 +185,45 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class Dist:
+    """The little of torch.distributed the bench needs, no-ops on one rank."""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor([float(v) for v in values], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN,
+                                        "sum": self.dist.ReduceOp.SUM}[op])
+        return [float(x) for x in t.tolist()]
+
+    def timed_device(self, fn, steps):
+        """K calls of fn bracketed by barrier + synchronize, CUDA events on the current stream, max over ranks."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.reduce([e0.elapsed_time(e1)], "max")[0] / steps
+
+    def timed_wall(self, fn, steps):
+        fn(); self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.barrier()
+        return 1e3 * self.reduce([time.perf_counter() - t0], "max")[0] / steps
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -170,8 +232,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from shapefromprojections_b200 import _lib, distributed, workloads
-    from shapefromprojections_b200.function import rasterizer as R
+    from shapefromprojections_b200 import _lib, distributed
 
     rank, world, local_rank = distributed.init_from_env()
     if not torch.cuda.is_available():
@@ -179,7 +240,26 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.lib()
+    D = Dist(torch, dist, world, dev)
+    if args.config == "cfg5":
+        line = bench_cfg5(args, torch, D, rank, world, local_rank, dev)
+    elif args.config == "cfg2":
+        line = bench_cfg2(args, torch, D, rank, world, local_rank, dev)
+    else:
+        line = bench_step(args, torch, dist, D, rank, world, local_rank, dev)
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
+
+# ----------------------------------------------------------------------------------------------
+# the headline: fused projection + residual + backward step, angles sharded over the ranks
+# ----------------------------------------------------------------------------------------------
+def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
+    from shapefromprojections_b200 import _lib, distributed, workloads
+    from shapefromprojections_b200.function import rasterizer as R
+    L = _lib.lib()
     wl = workloads.make_workload(args.config)
     H, W, NA = wl["H"], wl["W"], wl["nangles"]
     V, F = wl["verts"].shape[0], wl["faces"].shape[0]
@@ -198,7 +278,6 @@ def main():
     target, _, _ = R.project_forward(gd, gt, faces32, labels, mus, idx)
     phat = torch.empty_like(target)
     xch = distributed.GradientExchange(V, mus.numel(), dev)
-    stats = None
 
     def step():
         xch.zero_()
@@ -206,32 +285,42 @@ def main():
                                 grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
         xch.all_reduce()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step()
-    barrier()
+    D.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
+    launches0 = L.ctdr_launch_count()
+    ms_step = D.timed_device(step, args.steps)
+    launches = (L.ctdr_launch_count() - launches0) + args.steps * xch.kernels_per_exchange(world)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
     pixels = NA * H * W
     value = pixels / (ms_step / 1e3) / 1e9
-    loss_sum, n_valid = (float(x) for x in xch.scalars.tolist())
+    loss_sum, n_valid = xch.loss_sum_and_count()
+
+    # ---- stages of the step as they run inside it (events between the stages), max / min over the ranks ----
+    stages = None
+    if not args.no_breakdown:
+        acc, nrep = {}, 3
+        for _ in range(nrep):
+            xch.zero_()
+            R.project_residual_step(gd, verts, faces32, labels, mus, idx, target, phat=phat, grad_verts=xch.grad_verts,
+                                    grad_mus=xch.grad_mus, out2=xch.scalars, stage_ms=acc)
+        names = list(_lib.STAGES)
+        mine = [acc[n] / nrep for n in names]
+        # the exchange on its own: fill + all-reduce behind a barrier (launch + NCCL latency, 0.6 MB at cfg3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record()
+        for _ in range(10):
+            xch.zero_(); xch.all_reduce()
+        e1.record(); D.barrier()
+        mine.append(e0.elapsed_time(e1) / 10); names.append("zero_and_all_reduce")
+        mx, mn = D.reduce(mine, "max"), D.reduce(mine, "min")
+        stages = {f"{n}_ms": {"max_over_ranks": a, "min_over_ranks": b} for n, a, b in zip(names, mx, mn)}
+        stages["sum_of_stage_max_ms"] = sum(mx)
 
     # ---- end to end: host buffers in, host results out, every step -------------------------------
     e2e = None
@@ -243,31 +332,18 @@ def main():
         stepper = R.HostStepper(gd, faces32, labels, V, mus.numel(), Bl, windows=8)
 
         def reduce_fn(flat, out2):
-            if world > 1:
-                dist.all_reduce(flat); dist.all_reduce(out2)
-
-        def timed_loop(fn, n):
-            fn(); barrier()
-            t0 = time.perf_counter()
-            for _ in range(n):
-                fn()
-            barrier()
-            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            return 1e3 * float(dt.item()) / n
+            xch.all_reduce_tensors(flat, out2)
 
         n_e2e = max(2, min(args.steps, 5))
         # (1) every input from pinned host memory every step, gradients + loss back to the host
-        e2e_ms = timed_loop(lambda: stepper.step(h_verts, h_mus, h_idx, h_target, reduce_fn), n_e2e)
+        e2e_ms = D.timed_wall(lambda: stepper.step(h_verts, h_mus, h_idx, h_target, reduce_fn), n_e2e)
         assert abs(float(stepper.h_out2[0]) - loss_sum) <= 1e-6 * abs(loss_sum) + 1e-9, "e2e result differs"
-        h2d = world_sum(torch, dist, world, dev, stepper.h2d_bytes)
-        d2h = world_sum(torch, dist, world, dev, stepper.d2h_bytes)
+        h2d = int(D.reduce([stepper.h2d_bytes], "sum")[0])
+        d2h = int(D.reduce([stepper.d2h_bytes], "sum")[0])
 
         # (2) the reference's full-batch flow: target uploaded once before the loop (optimize.py:125-127);
         # per step only the mesh parameters / angle indices go up and loss + gradients come back
-        h_grad = torch.empty(xch.flat.shape, dtype=torch.float32).pin_memory()
-        h_scal = torch.empty(2, dtype=torch.float64).pin_memory()
+        h_grad = torch.empty(xch.flat.shape, dtype=xch.flat.dtype).pin_memory()
 
         def resident_step():
             v = h_verts.to(dev, non_blocking=True); m = h_mus.to(dev, non_blocking=True)
@@ -276,10 +352,10 @@ def main():
             R.project_residual_step(gd, v, faces32, labels, m, ix, target, phat=phat,
                                     grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
             xch.all_reduce()
-            h_grad.copy_(xch.flat, non_blocking=True); h_scal.copy_(xch.scalars, non_blocking=True)
+            h_grad.copy_(xch.flat, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-        res_ms = timed_loop(resident_step, n_e2e)
+        res_ms = D.timed_wall(resident_step, n_e2e)
         e2e = {"value": pixels / (e2e_ms / 1e3) / 1e9, "unit": "Gpix/s", "ms_per_step": e2e_ms, "steps": n_e2e,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "what": "pinned host verts/mus/idx_angles/target -> device (target streamed in 8 angle windows on a "
@@ -289,76 +365,227 @@ def main():
                                            "step verts/mus/idx_angles up, gradients + loss down"}}
         del h_target, stepper
 
-    # ---- per-kernel breakdown (staged entry points, CUDA events on the launching stream) ----------
-    breakdown = None
+    # ---- staged entry points (Rasterizer boundary, unlinked kernels) + counters: context for the stage numbers ----
+    staged = None
     if not args.no_breakdown and rank == 0:
-        breakdown = kernel_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, phat)
+        staged = staged_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src = peaks()
     alg_bytes = workloads.algorithmic_bytes(NA, H, W, V, F, world)
     achieved = alg_bytes / (ms_step / 1e3) / 1e9 / world          # GB/s per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "what": "algorithmic bytes of one step (8 B/pixel + mesh term) / step time, per GPU; "
-                        "dominant kernels listed in `kernels`"}
+                "what": "algorithmic bytes of one step (8 B/pixel + mesh term) / step time, per GPU; per-kernel "
+                        "figures in dominant_kernel / second_kernel (stage times measured inside the step)"}
     line = {"metric": METRIC, "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: {wl['desc']}", "angles_per_gpu": Bl, "V": V, "F": F,
                        "step": "projection + masked-L2 residual + backward over all angles + gradient all-reduce",
-                       "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)",
+                       "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)" if Bl * H * W * 8 > 2 * 126e6
+                                    else "inputs smaller than L2: the step streams its own 2 x B x H x W x 4 B of sinogram/target, nothing else is reused between steps",
                        "parallelism": f"angles sharded over {world} GPU(s) (rank r owns angles r, r+N, ...), mesh replicated"},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches) * world,
+            "gpu_launches_per_rank_per_step": launches / args.steps,
             "loss": loss_sum / max(n_valid, 1.0), "n_valid": n_valid}
     if e2e is not None:
         line["e2e"] = e2e
-    if breakdown is not None:
-        line["kernels"] = breakdown
-        if "raster_step_ms" in breakdown:
-            # the two raster sweeps are the step's dominant kernels (42 % / 39 % of it in the ncu launch list);
-            # both are timed live here through the staged C-ABI entry points (same kernels, unlinked: inside the
-            # fused step the forward also records its face batches, +5 %, and the residual/backward sweep replays
-            # them instead of walking its own lists, -25 %)
-            tj = None
-            tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-            if os.path.exists(tpath):
-                with open(tpath) as fh:
-                    tj = json.load(fh).get(args.config)
-                if not (tj and tj.get("angles") == Bl):
-                    tj = None
+    if stages is not None:
+        line["kernels"] = stages
+        tj = traffic_table(args.config, Bl)
 
-            def kernel_roofline(name, ms, nbytes, key):
-                return {"name": name, "ms": ms, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
-                        "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": tj.get(key) if tj else None,
-                        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch "
-                                          "(profiles/r1_ncu_cfg3_summary.md)"}
-            fwd = kernel_roofline("k_raster<MODE_FWD> (forward sweep: 4 B sinogram store per pixel)",
-                                  breakdown["raster_forward_ms"], 4 * Bl * H * W, "k_raster<MODE_FWD>")
-            bwd = kernel_roofline("k_raster residual + backward sweep (4 B phat + 4 B target per pixel; timed as the staged "
-                                  "MODE_BWD launch, same traversal)", breakdown["raster_step_ms"], 8 * Bl * H * W,
-                                  "k_raster<MODE_STEP>")
-            line["roofline"]["dominant_kernel"] = fwd
-            line["roofline"]["second_kernel"] = bwd
-            line["roofline"]["traffic"] = fwd["traffic"]
-    if not args.no_optimise and world == 1:
+        def kernel_roofline(name, ms, nbytes, key):
+            return {"name": name, "ms": ms, "algorithmic_bytes": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
+                    "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": tj.get(key) if tj else None,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/)"}
+        fwd = kernel_roofline("k_raster<MODE_FWD, linked> (forward sweep as it runs in the step: 4 B sinogram store per pixel)",
+                              stages["raster_forward_ms"]["max_over_ranks"], 4 * Bl * H * W, "k_raster<MODE_FWD>")
+        bwd = kernel_roofline("k_step_replay + k_raster<MODE_STEP> twin (residual + backward sweep as it runs in the step: "
+                              "4 B phat + 4 B target per pixel)", stages["raster_step_ms"]["max_over_ranks"], 8 * Bl * H * W,
+                              "k_step_replay")
+        line["roofline"]["dominant_kernel"] = fwd
+        line["roofline"]["second_kernel"] = bwd
+        line["roofline"]["traffic"] = fwd["traffic"]
+    if staged is not None:
+        line["staged_entry_points"] = staged
+    if world == 1:
         import contextlib
-        with contextlib.redirect_stdout(sys.stderr):       # the reference-style modules print; stdout carries the JSON line only
-            line["optimise_iteration"] = optimise_iteration(torch, args.optimise_iters)
-    if not args.no_cpu_baseline and world == 1:
-        gpix, dt, sample = cpu_reference_sample(wl)
-        line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": sample, "seconds": dt}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        if not args.no_reference_ext:
+            with contextlib.redirect_stdout(sys.stderr):
+                line["reference_cuda_ext"] = reference_cuda_ext(torch)
+        if not args.no_optimise:
+            with contextlib.redirect_stdout(sys.stderr):       # the reference-style modules print; stdout carries the JSON line only
+                line["optimise_iteration"] = optimise_iteration(torch, args.optimise_iters)
+        if not args.no_cpu_baseline:
+            gpix, dt, sample, threads = cpu_reference_sample(wl)
+            line["cpu_baseline"] = {"value": gpix, "unit": "Gpix/s", "cores": threads, "kind": "port",
+                                    "sample": sample, "seconds": dt}
+    return line
 
 
-LAUNCHES_PER_STEP = 7   # per angle window: vertex transform, face assemble (+ face and chunk boxes), super-region lists, raster forward (records batches), raster residual/backward replay, its fallback twin, vertex backward
+def traffic_table(config, angles):
+    """ncu DRAM traffic per launch, kept per round under profiles/ (newest first)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as fh:
+                tj = json.load(fh).get(config)
+            if tj and tj.get("angles") == angles:
+                return tj
+    return None
+
+
+def staged_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, reps=3):
+    """The same work through the staged (Rasterizer-boundary) C-ABI entry points: unlinked kernels that
+    materialise p6/len3/ff; plus the fragment / candidate counters of the forward sweep."""
+    from shapefromprojections_b200 import _lib
+    out = {}
+
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    try:
+        p6, len3, ff = R.vertex_forward(gd, verts, faces32, idx)
+        out["ctdr_vertex_forward_ms"] = timed(lambda: R.vertex_forward(gd, verts, faces32, idx))
+        out["ctdr_raster_forward_ms"] = timed(lambda: R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val))
+        im, _, st = R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val, want_stats=True)
+        g = (2.0 * (im.squeeze(-1) - target)).unsqueeze(-1).contiguous()
+        out["ctdr_raster_backward_ms"] = timed(lambda: R.raster_backward(g, im, p6, len3, ff, labels, mus, gd.max_sino_val))
+        st = st.tolist()
+        out["fragments"] = st[_lib.STAT_FRAGMENTS]; out["candidates"] = st[_lib.STAT_CANDIDATES]
+        out["nonpositive_len"] = st[_lib.STAT_NONPOSITIVE_LEN]; out["list_segments"] = st[_lib.STAT_LIST_SEGMENTS]
+        out["face_batches"] = st[4]; out["chunk_hits"] = st[5]
+        del p6, len3, ff, im, g
+        out["ctdr_project_forward_ms"] = timed(lambda: R.project_forward(gd, verts, faces32, labels, mus, idx))
+    except torch.cuda.OutOfMemoryError:
+        out["note"] = "staged breakdown skipped (out of memory)"
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's own CUDA extension on this GPU (north_star: "plus the reference's own CUDA extension on
+# one B200 where it builds"): context, like-for-like at the Rasterizer boundary
+# ----------------------------------------------------------------------------------------------
+def reference_cuda_ext(torch):
+    try:
+        from oracle import build_ref, time_ref_ext
+        mod = build_ref.load()
+    except Exception as exc:          # noqa: BLE001  (optional test infrastructure)
+        return {"unavailable": f"oracle/_ref could not be loaded: {exc}"}
+    if mod is None:
+        return {"unavailable": "oracle/_ref/cuda_diff_fp.so is not built (python oracle/build_ref.py in the build container)"}
+    return {"what": "reference kernels (ctdr/cuda/diff_fp_for.cu, diff_fp_back.cu compiled unmodified for sm_100a) through the "
+                    "host flow of ctdr/function/rasterizer.py:23-105 vs this library, same inputs at the Rasterizer boundary",
+            "cases": time_ref_ext.run_cases(mod)}
+
+
+# ----------------------------------------------------------------------------------------------
+# config 5: batched simulation, forward only, meshes sharded over the ranks (SURVEY.md section 8e)
+# ----------------------------------------------------------------------------------------------
+def bench_cfg5(args, torch, D, rank, world, local_rank, dev):
+    from shapefromprojections_b200 import _lib, workloads
+    from shapefromprojections_b200.function import rasterizer as R
+    L = _lib.lib()
+    wl = workloads.make_workload("cfg5")
+    H, W, NA, NM = wl["H"], wl["W"], wl["nangles"], wl["nmeshes"]
+    gd = R.GeometryDevice(wl["geom"], dev)
+    mine = list(range(rank, NM, world))                      # 8 meshes per GPU at N = 8; no collective
+    meshes = []
+    for i in mine:
+        v, f = workloads.cfg5_mesh(i)
+        meshes.append((torch.as_tensor(v, dtype=torch.float32).to(dev), torch.as_tensor(f).to(torch.int32).to(dev),
+                       torch.as_tensor(np.ascontiguousarray(v, dtype=np.float32)).pin_memory()))
+    F = int(meshes[0][1].shape[0]); V = int(meshes[0][0].shape[0])
+    labels = torch.as_tensor(wl["labels"]).to(dev); mus = torch.as_tensor(wl["mus"]).to(dev)
+    idx = torch.arange(NA, device=dev)
+    keep = {}
+
+    def step():
+        for v, f, _ in meshes:
+            keep["im"], _, _ = R.project_forward(gd, v, f, labels, mus, idx)
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.ctdr_launch_count()
+    ms_step = D.timed_device(step, args.steps)
+    launches = L.ctdr_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    pixels = NM * NA * H * W
+    value = pixels / (ms_step / 1e3) / 1e9
+    e2e = None
+    if not args.no_e2e:
+        # simulation_cone_beam.py:63-82 per mesh: vertices from the host, sinogram back to the host (.cpu().numpy())
+        h_out = torch.empty(NA, H, W, dtype=torch.float32).pin_memory()
+
+        def host_step():
+            for _, f, hv in meshes:
+                v = hv.to(dev, non_blocking=True)
+                im, _, _ = R.project_forward(gd, v, f, labels, mus, idx)
+                h_out.copy_(im, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        n = max(2, min(args.steps, 3))
+        e2e_ms = D.timed_wall(host_step, n)
+        e2e = {"value": pixels / (e2e_ms / 1e3) / 1e9, "unit": "Gpix/s", "ms_per_step": e2e_ms, "steps": n,
+               "h2d_bytes_per_step": NM * V * 12, "d2h_bytes_per_step": NM * NA * H * W * 4,
+               "what": "per mesh: pinned host vertices -> device, fused forward projection, full sinogram -> pinned host "
+                       "(simulation_cone_beam.py:82 copies every sinogram to the host): PCIe-bound"}
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    alg = 4 * pixels + NM * (12 * V + 12 * F + 8 * F) + 48 * NA * NM
+    achieved = alg / (ms_step / 1e3) / 1e9 / world
+    line = {"metric": "fwd detector Gpix/s (batched simulation, backprop=False)", "value": value, "unit": "Gpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg5: {wl['desc']}", "meshes_per_gpu": len(mine), "V": V, "F": F,
+                       "step": "forward projection of all 64 meshes (one fused call per mesh), no collective",
+                       "l2_policy": "each mesh writes a 377 MB sinogram (> 126 MB L2); meshes differ from call to call",
+                       "parallelism": f"meshes sharded over {world} GPU(s) (rank r owns meshes r, r+N, ...)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "what": "4 B sinogram store per pixel + mesh term, per GPU"},
+            "clocks": clocks, "gpu_launches": int(launches) * world, "gpu_launches_per_rank_per_step": launches / args.steps,
+            "sinogram_max": float(keep["im"].max())}
+    if e2e is not None:
+        line["e2e"] = e2e
+    return line
+
+
+# ----------------------------------------------------------------------------------------------
+# config 2: s per optimise iteration (BASELINE.json's second metric), 500 iterations by default
+# ----------------------------------------------------------------------------------------------
+def bench_cfg2(args, torch, D, rank, world, local_rank, dev):
+    if rank != 0:
+        return None
+    import contextlib
+    niter = 500 if args.steps == 10 else max(args.steps, 20)        # the configuration names 500 iterations
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    with contextlib.redirect_stdout(sys.stderr):
+        res = optimise_iteration(torch, niter)
+    clocks = sampler.stop()
+    return {"metric": "s per optimise iteration", "value": res["s_per_iteration_cuda_graph"], "unit": "s", "n_gpus": 1,
+            "steps": niter, "warmup": 10, "ms_per_step": 1e3 * res["s_per_iteration_cuda_graph"], "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": res["workload"], "step": "one full optimiser iteration (fused data term + sparse regularisers + "
+                       "Adam + mus clamp) replayed from a CUDA graph, one host sync per iteration for the loss (ctdr/optimize.py:193)",
+                       "l2_policy": "the whole problem (30x192x192 sinogram, 2562 vertices) is L2-resident by nature: this "
+                                    "metric is launch/latency-bound, not bandwidth-bound", "parallelism": "1 GPU"},
+            "e2e": {"value": res["s_per_iteration"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                    "what": "ctdr.optimize.run (the public loop, eager launches): target uploaded once like the reference "
+                            "(optimize.py:125-127), loss read back every iteration"},
+            "clocks": clocks, "optimise_iteration": res, "gpu_launches": res["ctdr_launches_graphed"]}
 
 
 def optimise_iteration(torch, niter):
@@ -368,11 +595,11 @@ def optimise_iteration(torch, niter):
     (fused data term + sparse regularisers + Adam), one host sync per iteration like the reference."""
     import tempfile
     import types
-    from shapefromprojections_b200 import optimize, workloads
+    from shapefromprojections_b200 import _lib, optimize, workloads
     from shapefromprojections_b200.dataset.dataset import SinoDataset
     from shapefromprojections_b200.function import rasterizer as R
     from shapefromprojections_b200.model.vanilla import Model
-    wl = workloads.make_workload("cfg1")                      # same geometry numbers as data/2bunnyA
+    wl = workloads.make_workload("cfg2")
     dev = torch.device("cuda", torch.cuda.current_device())
     gd = R.GeometryDevice(wl["geom"], dev)
     gt_v, gt_f = workloads.star_surface(4)
@@ -408,49 +635,12 @@ def optimise_iteration(torch, niter):
                         "wlap=10 wedge=2 wflat=0.01 lr=0.01 (parse_args.py defaults)",
             "s_per_iteration": dt / niter, "s_per_iteration_cuda_graph": dt_graph / niter, "l2_after_graphed": last[0],
             "iterations": niter, "l2_first": l2[0] if l2 else None,
-            "l2_last": l2[-1] if l2 else None, "mus": [float(x) for x in model.mus.detach().cpu()]}
+            "l2_last": l2[-1] if l2 else None, "mus": [float(x) for x in model.mus.detach().cpu()],
+            "ctdr_launches_graphed": int(git.ctdr_launches_per_iteration) * niter}
 
 
 def wl_pin(torch, arr):
     return torch.as_tensor(np.ascontiguousarray(arr)).pin_memory()
-
-
-def world_sum(torch, dist, world, dev, v):
-    t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t)
-    return int(t.item())
-
-
-def kernel_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target, phat, reps=3):
-    """Time the stages of one step through the staged C-ABI entry points (same kernels)."""
-    from shapefromprojections_b200 import _lib
-    out = {}
-
-    def timed(fn):
-        fn(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record(); torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-    try:
-        p6, len3, ff = R.vertex_forward(gd, verts, faces32, idx)
-        out["vertex_forward_ms"] = timed(lambda: R.vertex_forward(gd, verts, faces32, idx))
-        out["raster_forward_ms"] = timed(lambda: R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val))
-        im, _, st = R.raster_forward(p6, len3, ff, labels, mus, gd.H, gd.W, gd.max_sino_val, want_stats=True)
-        g = (2.0 * (im.squeeze(-1) - target)).unsqueeze(-1).contiguous()
-        out["raster_backward_ms"] = timed(lambda: R.raster_backward(g, im, p6, len3, ff, labels, mus, gd.max_sino_val))
-        out["raster_step_ms"] = out["raster_backward_ms"]
-        st = st.tolist()
-        out["fragments"] = st[_lib.STAT_FRAGMENTS]; out["candidates"] = st[_lib.STAT_CANDIDATES]
-        out["nonpositive_len"] = st[_lib.STAT_NONPOSITIVE_LEN]; out["list_segments"] = st[_lib.STAT_LIST_SEGMENTS]
-        out["face_batches"] = st[4]; out["chunk_hits"] = st[5]
-        out["full_forward_ms"] = timed(lambda: R.project_forward(gd, verts, faces32, labels, mus, idx))
-    except torch.cuda.OutOfMemoryError:
-        out["note"] = "staged breakdown skipped (out of memory)"
-    return out
 
 
 if __name__ == "__main__":

@@ -36,7 +36,8 @@
 extern "C" {
 #endif
 
-#define CTDR_ABI_VERSION 2   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi */
+#define CTDR_ABI_VERSION 3   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi; 3: + ctdr_launch_count,
+                                ctdr_project_residual_step_timed */
 
 /* argument errors */
 #define CTDR_E_NULL      (-1)   /* a required pointer is NULL */
@@ -68,6 +69,14 @@ typedef struct CUstream_st* ctdr_stream_t;   /* == cudaStream_t */
 
 int         ctdr_abi_version(void);
 const char* ctdr_last_error(void);
+
+/* Number of kernels this library has launched so far in the process (all threads, all streams); measurement
+ * aid: the difference around a timed region is the region's launch count. */
+unsigned long long ctdr_launch_count(void);
+
+/* Tuning / debug overrides come from the environment (CTDR_REGION_TILES, CTDR_REGION_MAJOR, CTDR_DIRECT_MAX_BOX,
+ * CTDR_NO_BATCH_RECORDS), read once at first use; this re-reads them (tests and tuning scripts). */
+void ctdr_tuning_reload(void);
 
 /* Self-test of the one arithmetic shortcut the kernels take: fl32(k1/(k3+1e-15)) through the
  * per-face reciprocal + one fused correction step vs the IEEE fp64 division of the reference
@@ -154,7 +163,8 @@ int ctdr_raster_backward(const float* grad_im, const float* im,
  * and their autograd.
  *   geom       angles[nangles] (PARALLEL3D) or Vectors[nangles,12] (the *_VEC kinds), float32,
  *              exactly the array the reference uploads (fp_opengl.py:63, fp_vecs.py:64)
- *   idx_angles [B] int64 rows of `geom` to project
+ *   idx_angles [B] int64 rows of `geom` to project; a row outside [0, nangles) turns that angle's outputs into NaN
+ *              (the reference raises IndexError, fp_vecs.py:101; Python callers validate host indices beforehand)
  *   verts [V,3] float32, faces [F,3] int32
  *   spacing_x/y: DetectorSpacingX/Y as the Python doubles of proj_geom (PARALLEL3D only: they
  *              define the orthographic matrix, projection.py:65-80, evaluated in double and
@@ -240,6 +250,28 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles,
                                const int32_t* vadj_start, const int32_t* vadj_corner,
                                void* workspace, size_t workspace_bytes,
                                int64_t* stats, unsigned flags, ctdr_stream_t stream);
+
+/* Profiling variant of ctdr_project_residual_step: same work, same results, plus the device time of every
+ * stage, measured with CUDA events recorded on `stream` between the stages (summed over the angle windows).
+ * It SYNCHRONISES with the stream before returning (the one entry point that does) and writes
+ * stage_ms_host[CTDR_STAGE_COUNT] (HOST memory, milliseconds). */
+#define CTDR_STAGE_VERTEX_FORWARD  0  /* vertex transform + face assembly (p6/len3/ff, pixel boxes) + super-region lists */
+#define CTDR_STAGE_RASTER_FORWARD  1  /* forward sweep (records its face batches) */
+#define CTDR_STAGE_MEMSET          2  /* gradient-window and record-cursor memsets */
+#define CTDR_STAGE_RASTER_STEP     3  /* residual + backward sweep: replay kernel + the walk kernel for unrecorded regions */
+#define CTDR_STAGE_VERTEX_BACKWARD 4  /* transposed vertex stage into grad_verts */
+#define CTDR_STAGE_COUNT           5
+int ctdr_project_residual_step_timed(int geom_kind, const float* geom, int nangles,
+                                     const int64_t* idx_angles, int B,
+                                     const float* verts, int V, const int32_t* faces, int F,
+                                     const int32_t* labels2, const float* mus, int n_mus,
+                                     int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                                     const float* target, float* phat,
+                                     float* grad_verts, float* grad_mus, double* out2,
+                                     const int32_t* vadj_start, const int32_t* vadj_corner,
+                                     void* workspace, size_t workspace_bytes,
+                                     int64_t* stats, unsigned flags, ctdr_stream_t stream,
+                                     float* stage_ms_host);
 
 #ifdef __cplusplus
 }

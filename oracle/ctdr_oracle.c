@@ -40,4 +40,11 @@
 #undef NAME
 #undef FMA
 
-int oracle_abi_version(void) { return 1; }
+int oracle_abi_version(void) { return 2; }
+
+/* Thread control for the timed CPU baseline: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+ * silently time the "all host cores" arm on one core; bench.py sets the count explicitly and reports what
+ * the OpenMP runtime actually uses. */
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }

@@ -55,13 +55,11 @@ def ours_fwd_bwd(p6, len3, ff, labels, mus, H, W, msv, g):
     return im, dldp, dldf, dldmu
 
 
-def main():
-    m = build_ref.load()
-    if m is None:
-        print(json.dumps({"unavailable": "oracle/_ref/cuda_diff_fp.so is not built"}))
-        return
-    dev = torch.device("cuda", 0)
-    for name, nang, reps in (("cfg1", None, 5), ("cfg3", 4, 1)):
+def run_cases(m, cases=(("cfg1", None, 5), ("cfg3", 4, 1))):
+    """[(workload, angles or None = all, repetitions of the reference)] -> list of result dicts."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = []
+    for name, nang, reps in cases:
         wl = make_workload(name)
         gd = R.GeometryDevice(wl["geom"], dev)
         v = torch.as_tensor(wl["verts"]).to(dev); f32 = torch.as_tensor(wl["faces"]).to(torch.int32).to(dev)
@@ -76,10 +74,20 @@ def main():
         pix = nang * H * W
         same = bool(torch.equal(o_ref[0], o_new[0]))
         gerr = float((o_ref[1] - o_new[1]).norm() / o_ref[1].norm())
-        print(json.dumps({"case": f"{name}: {nang} angle(s) x {H} x {W}, F={f32.shape[0]}, Rasterizer boundary, fwd (pass 1 + pass 2) + bwd",
-                          "reference_cuda_extension_ms": t_ref, "this_repo_ms": t_new, "ratio": t_ref / t_new,
-                          "reference_Gpix_per_s": pix / t_ref / 1e6, "this_repo_Gpix_per_s": pix / t_new / 1e6,
-                          "sinogram_bit_identical": same, "grad_p6_rel_diff": gerr}))
+        out.append({"case": f"{name}: {nang} angle(s) x {H} x {W}, F={f32.shape[0]}, Rasterizer boundary, fwd (pass 1 + pass 2) + bwd",
+                    "reference_cuda_extension_ms": t_ref, "this_repo_ms": t_new, "ratio": t_ref / t_new,
+                    "reference_Gpix_per_s": pix / t_ref / 1e6, "this_repo_Gpix_per_s": pix / t_new / 1e6,
+                    "sinogram_bit_identical": same, "grad_p6_rel_diff": gerr})
+    return out
+
+
+def main():
+    m = build_ref.load()
+    if m is None:
+        print(json.dumps({"unavailable": "oracle/_ref/cuda_diff_fp.so is not built"}))
+        return
+    for res in run_cases(m):
+        print(json.dumps(res))
 
 
 if __name__ == "__main__":

@@ -71,15 +71,19 @@ def main(rep, lib, src_path):
         sass = S.sass_lines(lib, ksub)
         h = blk["hdr"]
         ie, sm = h.index("Instructions Executed"), h.index("# Samples")
-        regions = defaultdict(lambda: [0, 0])
-        tot = [0, 0]
+        te, pe = h.index("Thread Instructions Executed"), h.index("Predicated-On Thread Instructions Executed")
+        regions = defaultdict(lambda: [0, 0, 0, 0])
+        tot = [0, 0, 0, 0]
         for r, s in zip(blk["rows"], sass):
             k = region(s[2])
-            regions[k][0] += int(r[ie]); regions[k][1] += int(r[sm])
-            tot[0] += int(r[ie]); tot[1] += int(r[sm])
-        print(f"{blk['name']}: {tot[0]:.4g} warp-instructions, {tot[1]} stall samples ({len(blk['rows'])} SASS instructions)")
-        for k, (i, s) in sorted(regions.items(), key=lambda kv: -kv[1][0]):
-            print(f"  {k:58s} inst {100 * i / tot[0]:6.2f} %   samples {100 * s / tot[1]:6.2f} %")
+            for j, col in enumerate((ie, sm, te, pe)):
+                regions[k][j] += int(r[col]); tot[j] += int(r[col])
+        print(f"{blk['name']}: {tot[0]:.4g} warp-instructions, {tot[1]} stall samples ({len(blk['rows'])} SASS instructions); "
+              f"threads per instruction {tot[2] / tot[0]:.1f} active, {tot[3] / tot[0]:.1f} predicated-on "
+              f"(smsp__thread_inst_executed_per_inst_executed)")
+        for k, (i, s, t, p) in sorted(regions.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:58s} inst {100 * i / tot[0]:6.2f} %   samples {100 * s / tot[1]:6.2f} %   "
+                  f"threads/inst {t / max(i, 1):5.1f} active {p / max(i, 1):5.1f} pred-on")
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include "ctdr_raster.cuh"
 #include "ctdr_vertex.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -36,7 +37,62 @@ int cuda_fail(cudaError_t e, const char* where) {
         if (e__ != cudaSuccess) return cuda_fail(e__, where);    \
     } while (0)
 
+// every kernel launch of the library is counted (ctdr_launch_count): bench.py reports the launches inside its
+// timed region from this counter instead of a constant
+std::atomic<unsigned long long> g_launches{0};
+#define CTDR_LAUNCHED(n, where)                                  \
+    do {                                                         \
+        g_launches.fetch_add((n), std::memory_order_relaxed);    \
+        CTDR_CUDA(cudaGetLastError(), where);                    \
+    } while (0)
+
+// Optional per-stage device timing of the residual step (ctdr_project_residual_step_timed): events recorded on
+// the caller's stream between the stages; elapsed times are read after one synchronisation at the end.
+struct StageTimer {
+    static constexpr int MAX_MARKS = 512;
+    cudaEvent_t ev[MAX_MARKS];
+    int stage[MAX_MARKS];
+    int n = 0;
+    bool ok = true;
+    void mark(int stage_id, cudaStream_t st) {
+        if (n >= MAX_MARKS) { ok = false; return; }
+        if (cudaEventCreate(&ev[n]) != cudaSuccess || cudaEventRecord(ev[n], st) != cudaSuccess) { ok = false; return; }
+        stage[n++] = stage_id;
+    }
+    // stage_ms[k] += time between the mark that closes stage k and the mark before it
+    void collect(float* stage_ms, int nstages) {
+        if (n > 0) cudaEventSynchronize(ev[n - 1]);
+        for (int i = 1; i < n; ++i) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[i - 1], ev[i]) == cudaSuccess && stage[i] >= 0 && stage[i] < nstages) stage_ms[stage[i]] += ms;
+        }
+        for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+        n = 0;
+    }
+};
+#define CTDR_MARK(tm, id, st) do { if (tm) (tm)->mark((id), (st)); } while (0)
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tuning / debug overrides.  The environment is read ONCE (first use, or ctdr_tuning_reload()), never per launch:
+// behaviour does not follow ambient changes of the environment behind the caller's back.
+struct Tuning {
+    int region_tiles = 0;        // CTDR_REGION_TILES: 2, 4 or 8; 0 = heuristic
+    int region_major = 1;        // CTDR_REGION_MAJOR: CTA order of k_raster (measured: 1 wins)
+    int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
+    bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
+    void load() {
+        *this = Tuning();
+        if (const char* e = getenv("CTDR_REGION_TILES")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) region_tiles = v; }
+        if (const char* e = getenv("CTDR_REGION_MAJOR")) region_major = atoi(e) != 0;
+        if (const char* e = getenv("CTDR_DIRECT_MAX_BOX")) direct_max_box = atoi(e) < 0 ? -1 : atoi(e);
+        no_batch_records = getenv("CTDR_NO_BATCH_RECORDS") != nullptr;
+    }
+};
+Tuning& tuning() {
+    static Tuning t = [] { Tuning x; x.load(); return x; }();
+    return t;
+}
 
 int check_sizes(int B, int F, int H, int W, int n_mus) {
     if (B <= 0 || F <= 0 || H <= 0 || W <= 0 || n_mus <= 0)
@@ -48,10 +104,7 @@ int check_sizes(int B, int F, int H, int W, int n_mus) {
 }
 
 int pick_region_tiles(int B, int F, int H, int W) {
-    if (const char* env = getenv("CTDR_REGION_TILES")) {      // tuning/debug override: 2, 4 or 8
-        const int v = atoi(env);
-        if (v == 2 || v == 4 || v == 8) return v;
-    }
+    if (tuning().region_tiles) return tuning().region_tiles;      // tuning/debug override: 2, 4 or 8
     // One CTA per region of RT x RT tiles.  8x8 amortises the per-CTA list build best; 4x4 gives four
     // times more CTAs, which wins when the grid is small (multi-GPU angle shards: tail effect) or when
     // region lists are long (very fine meshes: fewer list segments).  Measured on config 3 / north star.
@@ -74,8 +127,7 @@ void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
     P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
     P.chunk_box = boxes;
-    P.region_major = 1;     // measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3)
-    if (const char* env = getenv("CTDR_REGION_MAJOR")) P.region_major = atoi(env) != 0;
+    P.region_major = tuning().region_major;     // 1 measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3)
     P.sr_rx = (P.regions_x + MAX_SR - 1) / MAX_SR;
     P.sr_ry = (P.regions_y + MAX_SR - 1) / MAX_SR;
     P.nsr_x = (P.regions_x + P.sr_rx - 1) / P.sr_rx;
@@ -88,7 +140,7 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
         const long long blocks = (warps + WARPS - 1) / WARPS;
         if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
         k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
-        CTDR_CUDA(cudaGetLastError(), "k_chunk_bbox launch");
+        CTDR_LAUNCHED(1, "k_chunk_bbox launch");
     }
     if (P.slist) {      // tile-binned modes: coarse (super-region) lists for phase A of k_raster
         const long long sblocks = (long long)P.B * P.nsr_x * P.nsr_y;
@@ -96,7 +148,7 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
         k_super_lists<<<(unsigned)sblocks, THREADS, 0, st>>>(boxes, P.NC, P.H, P.W, P.nsr_x, P.nsr_y,
                                                              P.sr_rx * P.RT * TILE, P.sr_ry * P.RT * TILE,
                                                              const_cast<int*>(P.slist), const_cast<int*>(P.scount));
-        CTDR_CUDA(cudaGetLastError(), "k_super_lists launch");
+        CTDR_LAUNCHED(1, "k_super_lists launch");
     }
     return 0;
 }
@@ -120,22 +172,28 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool l
     const size_t smem = (MODE == MODE_MULTI)
         ? gram_bytes + (P.n_out > 2 ? (size_t)WARPS * (MAX_OUT - 2) * TILE_PIX * sizeof(float) : 0)
         : raster_smem_bytes(P.n_mus);
-    constexpr bool SWEEP = (MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP);
-    constexpr bool LINKABLE = (MODE == MODE_FWD || MODE == MODE_STEP);
-    constexpr int MS = SWEEP ? MODE : MODE_FWD, ML = LINKABLE ? MODE : MODE_FWD;   // keep unused branches instantiable
-    // fine meshes (about a pixel per face): batches of small boxes are walked face-per-lane (DIRECT)
-    const bool direct = SWEEP && P.direct_max_box > 0;
+    // fine meshes (about a pixel per face): the forward walks batches of small boxes face-per-lane (DIRECT); the
+    // backward modes walk row spans face-per-lane in any case (process_batch_rows)
+    const bool direct = MODE == MODE_FWD && P.direct_max_box > 0;
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate (never linked)
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-    } else if (linked && LINKABLE) {
-        if (direct) launch_raster_variant<ML, true, true>(P, (unsigned)blocks, smem, st);
-        else launch_raster_variant<ML, false, true>(P, (unsigned)blocks, smem, st);
-    } else if (direct) {
-        launch_raster_variant<MS, true, false>(P, (unsigned)blocks, smem, st);
+    } else if (linked && MODE == MODE_STEP) {
+        // replay-only residual/backward kernel over the batches the forward sweep recorded
+        if (P.stats) k_step_replay<true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        else k_step_replay<false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+    } else if constexpr (MODE == MODE_FWD) {
+        if (linked) {
+            if (direct) launch_raster_variant<MODE_FWD, true, true>(P, (unsigned)blocks, smem, st);
+            else launch_raster_variant<MODE_FWD, false, true>(P, (unsigned)blocks, smem, st);
+        } else if (direct) {
+            launch_raster_variant<MODE_FWD, true, false>(P, (unsigned)blocks, smem, st);
+        } else {
+            launch_raster_variant<MODE_FWD, false, false>(P, (unsigned)blocks, smem, st);
+        }
     } else {
         launch_raster_variant<MODE, false, false>(P, (unsigned)blocks, smem, st);
     }
-    CTDR_CUDA(cudaGetLastError(), "k_raster launch");
+    CTDR_LAUNCHED(1, "k_raster launch");
     return 0;
 }
 
@@ -349,7 +407,7 @@ RasterParams base_params(const float* p6, const float* ff, const float* len3, co
     // detector, F >= 0.4*H*W means an average projected face of at most ~1.5 pixels (measured: north-star mesh,
     // 1M faces on 1024^2, -9 %; config 3, 100k faces, +3 % — hence a per-call choice, not a per-batch one).
     P.direct_max_box = ((double)F >= 0.4 * (double)H * (double)W) ? 64 : 0;
-    if (const char* env = getenv("CTDR_DIRECT_MAX_BOX")) P.direct_max_box = atoi(env);   // tuning/debug override; 0 disables
+    if (tuning().direct_max_box >= 0) P.direct_max_box = tuning().direct_max_box;   // tuning/debug override; 0 disables
     return P;
 }
 
@@ -360,9 +418,9 @@ int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream
         if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
         if (flags & CTDR_FLAG_NO_PREFILTER) k_backward_faceowner<false, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
         else k_backward_faceowner<true, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
-        CTDR_CUDA(cudaGetLastError(), "k_backward_faceowner launch");
+        CTDR_LAUNCHED(1, "k_backward_faceowner launch");
         k_mus_reduce<<<P.n_mus, 1024, 0, st>>>(ws.fs, P.labels2, P.B, P.F, P.n_mus, P.grad_mus);
-        CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
+        CTDR_LAUNCHED(1, "k_mus_reduce launch");
         return 0;
     }
     fill_decomposition(P, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
@@ -371,11 +429,11 @@ int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream
     return launch_raster<MODE_BWD>(P, flags, st);
 }
 
-VertexParams vertex_params(int kind, const float* geom, const int64_t* idx, int B, const float* verts, int V,
+VertexParams vertex_params(int kind, const float* geom, int nangles, const int64_t* idx, int B, const float* verts, int V,
                            const int32_t* faces, int F, int H, int W, double sx, double sy, double msv) {
     VertexParams P;
     memset(&P, 0, sizeof(P));
-    P.kind = kind; P.geom = geom; P.idx_angles = reinterpret_cast<const long long*>(idx);
+    P.kind = kind; P.geom = geom; P.nangles = nangles; P.idx_angles = reinterpret_cast<const long long*>(idx);
     P.B = B; P.V = V; P.F = F; P.H = H; P.W = W; P.verts = verts; P.faces = faces;
     P.msv = (float)msv;
     if (kind == CTDR_GEOM_PARALLEL3D) {
@@ -469,7 +527,7 @@ int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* 
     const long long blocks = (n + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
     k_vertex_forward<<<(unsigned)blocks, 256, 0, st>>>(P, p6, len3, ff);
-    CTDR_CUDA(cudaGetLastError(), "k_vertex_forward launch");
+    CTDR_LAUNCHED(1, "k_vertex_forward launch");
     return 0;
 }
 
@@ -480,9 +538,9 @@ int launch_vertex_forward_staged(const VertexParams& P, float4* vt, const int32_
     if ((nv + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*V too large for one launch");
     if (P.B > 65535) return fail(CTDR_E_SHAPE, "angle window of %d angles > 65535", P.B);
     k_vertex_transform<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(P, vt);
-    CTDR_CUDA(cudaGetLastError(), "k_vertex_transform launch");
+    CTDR_LAUNCHED(1, "k_vertex_transform launch");
     k_face_assemble<<<dim3((unsigned)((P.F + 255) / 256), (unsigned)P.B), 256, 0, st>>>(P, vt, labels2, p6, len3, ff, face_boxes, chunk_boxes);
-    CTDR_CUDA(cudaGetLastError(), "k_face_assemble launch");
+    CTDR_LAUNCHED(1, "k_face_assemble launch");
     return 0;
 }
 
@@ -495,7 +553,7 @@ int launch_vertex_backward(const VertexParams& P, const float* gp6, const float*
     const int per = (P.B + slices - 1) / slices;
     dim3 grid((unsigned)face_blocks, (unsigned)((P.B + per - 1) / per));
     k_vertex_backward<<<grid, 256, 0, st>>>(P, gp6, glen3, grad_verts, per);
-    CTDR_CUDA(cudaGetLastError(), "k_vertex_backward launch");
+    CTDR_LAUNCHED(1, "k_vertex_backward launch");
     return 0;
 }
 
@@ -517,11 +575,11 @@ int deterministic_window(RasterParams P, const VertexParams& VP, const ProjectWs
         if (exact) k_backward_faceowner<false, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
         else k_backward_faceowner<true, false><<<(unsigned)blocks, 128, 0, st>>>(P, ws.fs);
     }
-    CTDR_CUDA(cudaGetLastError(), "k_backward_faceowner launch");
+    CTDR_LAUNCHED(resid ? 3 : 1, "k_backward_faceowner launch");
     k_mus_reduce<<<P.n_mus, 1024, 0, st>>>(ws.fs, P.labels2, P.B, P.F, P.n_mus, P.grad_mus);
-    CTDR_CUDA(cudaGetLastError(), "k_mus_reduce launch");
+    CTDR_LAUNCHED(1, "k_mus_reduce launch");
     k_vertex_backward_gather<<<(VP.V + 127) / 128, 128, 0, st>>>(VP, vstart, vcorner, ws.gp6, ws.glen3, grad_verts);
-    CTDR_CUDA(cudaGetLastError(), "k_vertex_backward_gather launch");
+    CTDR_LAUNCHED(1, "k_vertex_backward_gather launch");
     return 0;
 }
 
@@ -536,7 +594,7 @@ int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned l
     const int blocks = 148 * 8, threads = 256;
     const unsigned long long per = (samples + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
     k_selftest_quotient<<<blocks, threads, 0, stream>>>(per, seed, mismatches);
-    CTDR_CUDA(cudaGetLastError(), "k_selftest_quotient launch");
+    CTDR_LAUNCHED(1, "k_selftest_quotient launch");
     return 0;
 }
 const char* ctdr_last_error(void) { return g_err; }
@@ -634,12 +692,11 @@ int ctdr_vertex_forward(int geom_kind, const float* geom, int nangles, const int
                         const float* verts, int V, const int32_t* faces, int F, int H, int W,
                         double spacing_x, double spacing_y, double max_sino_val,
                         float* p6, float* len3, float* ff, ctdr_stream_t stream) {
-    (void)nangles;
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, 1)) return rc;
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !p6 || !len3 || !ff) return fail(CTDR_E_NULL, "ctdr_vertex_forward: null pointer");
-    const VertexParams P = vertex_params(geom_kind, geom, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    const VertexParams P = vertex_params(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
     return launch_vertex_forward(P, p6, len3, ff, stream);
 }
 
@@ -647,12 +704,11 @@ int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles, const in
                          const float* verts, int V, const int32_t* faces, int F, int H, int W,
                          double spacing_x, double spacing_y, double max_sino_val,
                          const float* grad_p6, const float* grad_len3, float* grad_verts, ctdr_stream_t stream) {
-    (void)nangles;
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, 1)) return rc;
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !grad_p6 || !grad_len3 || !grad_verts) return fail(CTDR_E_NULL, "ctdr_vertex_backward: null pointer");
-    const VertexParams P = vertex_params(geom_kind, geom, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    const VertexParams P = vertex_params(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
     return launch_vertex_backward(P, grad_p6, grad_len3, grad_verts, stream);
 }
 
@@ -672,7 +728,6 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
                          double spacing_x, double spacing_y, double max_sino_val,
                          float* im, int32_t* cnt, void* workspace, size_t workspace_bytes,
                          int64_t* stats, unsigned flags, ctdr_stream_t stream) {
-    (void)nangles;
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
@@ -682,7 +737,7 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im + (size_t)b0 * hw;
@@ -701,7 +756,6 @@ int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, co
                                float* im_kxbxhxw, const float* target, double* gram,
                                void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                                ctdr_stream_t stream) {
-    (void)nangles;
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
     if (int rc = check_multi(n_out, n_mus, target, gram)) return rc;
@@ -714,7 +768,7 @@ int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, co
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus_kxn, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im_kxbxhxw + (size_t)b0 * hw; P.n_out = n_out; P.out_stride = (long long)B * (long long)hw;
@@ -726,7 +780,7 @@ int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, co
     return 0;
 }
 
-static int project_backward_impl(int geom_kind, const float* geom, const int64_t* idx_angles, int B,
+static int project_backward_impl(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
                                  const float* verts, int V, const int32_t* faces, int F,
                                  const int32_t* labels2, const float* mus, int n_mus, int H, int W,
                                  double spacing_x, double spacing_y, double max_sino_val,
@@ -742,7 +796,7 @@ static int project_backward_impl(int geom_kind, const float* geom, const int64_t
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
         CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
@@ -779,25 +833,24 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles, const i
                           const int32_t* vadj_start, const int32_t* vadj_corner,
                           void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
                           ctdr_stream_t stream) {
-    (void)nangles;
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !grad_im || !im || !grad_verts || !grad_mus || !workspace)
         return fail(CTDR_E_NULL, "ctdr_project_backward: null pointer");
-    return project_backward_impl(geom_kind, geom, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
+    return project_backward_impl(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
                                  spacing_x, spacing_y, max_sino_val, grad_im, im, nullptr, nullptr,
                                  grad_verts, grad_mus, vadj_start, vadj_corner, workspace, workspace_bytes, stats, flags, stream);
 }
 
-int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
-                               const float* verts, int V, const int32_t* faces, int F,
-                               const int32_t* labels2, const float* mus, int n_mus, int H, int W,
-                               double spacing_x, double spacing_y, double max_sino_val,
-                               const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
-                               const int32_t* vadj_start, const int32_t* vadj_corner,
-                               void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
-                               ctdr_stream_t stream) {
+static int residual_step_impl(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                              const float* verts, int V, const int32_t* faces, int F,
+                              const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                              double spacing_x, double spacing_y, double max_sino_val,
+                              const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                              const int32_t* vadj_start, const int32_t* vadj_corner,
+                              void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                              cudaStream_t stream, StageTimer* tm) {
     if (int rc = check_geom(geom_kind)) return rc;
     if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
@@ -811,24 +864,29 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
     ProjectWs ws;
     if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
     const size_t hw = (size_t)H * W;
+    CTDR_MARK(tm, -1, stream);
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
+        CTDR_MARK(tm, CTDR_STAGE_VERTEX_FORWARD, stream);
         P.im = phat + (size_t)b0 * hw;
         if (!det) {             // the forward sweep records its face batches for the residual/backward sweep
             P.bmode = 1; P.brec = ws.brec; P.bhead = ws.bhead; P.btail = ws.btail; P.bflag = ws.bflag; P.bcursor = ws.bcursor; P.bcap = ws.bcap;
-            if (getenv("CTDR_NO_BATCH_RECORDS") || (flags & CTDR_FLAG_NO_PREFILTER)) P.bmode = 0;   // tuning/debug: no linking
+            if (tuning().no_batch_records || (flags & CTDR_FLAG_NO_PREFILTER)) P.bmode = 0;   // tuning/debug: no linking
             if (P.bmode) CTDR_CUDA(cudaMemsetAsync(ws.bcursor, 0, (size_t)nb * sizeof(int), stream), "memset record cursors");
         }
         const bool linked = P.bmode == 1;
+        CTDR_MARK(tm, CTDR_STAGE_MEMSET, stream);
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream, linked)) return rc;
+        CTDR_MARK(tm, CTDR_STAGE_RASTER_FORWARD, stream);
         if (linked) P.bmode = 2;
         CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
         CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        CTDR_MARK(tm, CTDR_STAGE_MEMSET, stream);
         P.im = nullptr;
         P.im_in = phat + (size_t)b0 * hw;
         P.target = target + (size_t)b0 * hw;
@@ -838,15 +896,55 @@ int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, co
         P.stats = nullptr;                                   // counters describe the forward sweep only
         if (det) {
             if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, true, flags, stream)) return rc;
+            CTDR_MARK(tm, CTDR_STAGE_RASTER_STEP, stream);
             continue;
         }
         // linked sweeps: the replay-only kernel takes the recorded regions, the ordinary one the rest
         if (linked) { if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc; }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
+        CTDR_MARK(tm, CTDR_STAGE_RASTER_STEP, stream);
         if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
+        CTDR_MARK(tm, CTDR_STAGE_VERTEX_BACKWARD, stream);
     }
-    (void)nangles;
     return 0;
 }
+
+int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                               const float* verts, int V, const int32_t* faces, int F,
+                               const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                               double spacing_x, double spacing_y, double max_sino_val,
+                               const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                               const int32_t* vadj_start, const int32_t* vadj_corner,
+                               void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                               ctdr_stream_t stream) {
+    return residual_step_impl(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
+                              spacing_x, spacing_y, max_sino_val, target, phat, grad_verts, grad_mus, out2,
+                              vadj_start, vadj_corner, workspace, workspace_bytes, stats, flags, stream, nullptr);
+}
+
+int ctdr_project_residual_step_timed(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                                     const float* verts, int V, const int32_t* faces, int F,
+                                     const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                                     double spacing_x, double spacing_y, double max_sino_val,
+                                     const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                                     const int32_t* vadj_start, const int32_t* vadj_corner,
+                                     void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                                     ctdr_stream_t stream, float* stage_ms_host) {
+    if (!stage_ms_host) return fail(CTDR_E_NULL, "ctdr_project_residual_step_timed: stage_ms_host is NULL");
+    for (int k = 0; k < CTDR_STAGE_COUNT; ++k) stage_ms_host[k] = 0.0f;
+    StageTimer tm;
+    const int rc = residual_step_impl(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, labels2, mus, n_mus, H, W,
+                                      spacing_x, spacing_y, max_sino_val, target, phat, grad_verts, grad_mus, out2,
+                                      vadj_start, vadj_corner, workspace, workspace_bytes, stats, flags, stream, &tm);
+    const bool ok = tm.ok;
+    tm.collect(stage_ms_host, CTDR_STAGE_COUNT);          // synchronises with the last recorded event
+    if (rc) return rc;
+    if (!ok) return fail(CTDR_E_SHAPE, "ctdr_project_residual_step_timed: more than %d stage marks (too many angle windows)", StageTimer::MAX_MARKS);
+    return 0;
+}
+
+unsigned long long ctdr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void ctdr_tuning_reload(void) { tuning().load(); }
 
 }  // extern "C"

@@ -582,11 +582,13 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Replay of recorded batches (residual/backward sweep): the next record is fetched into a landing zone in
 // the part of the forward/backward union the backward does not use (behind the three moment rows), while
 // the current batch is being processed.
-__device__ __forceinline__ int* record_landing(WarpSmem& S) { return reinterpret_cast<int*>(S.f.hitm + 128); }
+__device__ __forceinline__ int* record_landing(WarpSmem& S) { return S.cntv; }   // the count tile is unused by the backward modes
 __device__ __forceinline__ void prefetch_record(const RasterParams& P, WarpSmem& S, int off, int lane) {
     const int* r = P.brec + (long long)off * BREC_INTS;
     int* L = record_landing(S);
@@ -1085,6 +1087,261 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward batch (MODE_BWD / MODE_STEP): lane per face, row spans + per-row prefix sums.
+//
+// The gradients of a face need three sums over its covered pixels only (face_grads_from_moments):
+// sum g, sum g*k1, sum g*k2, and k1 = q*(x-ax) - n*(y-ay), k2 = m*(y-ay) - p*(x-ax) are affine in the pixel
+// position, so sum g, sum g*x, sum g*y suffice.  On one detector row a triangle covers an interval, so with
+// the exclusive prefix sums E0 = sum g and E1 = sum g*x along every row of the tile (built once per tile)
+// a (face, row) pair costs four shared-memory loads instead of one exact coverage test per pixel.
+// The interval comes from the same linear inequalities as the forward's conservative spans, with a margin
+// (1e-4 px + the rounding of the estimate and of the reference's own k1/k2/w0, times ~10) on BOTH sides:
+// pixels farther inside than the margin are certainly counted by the reference, pixels farther outside are
+// certainly not; only a pixel centre within the margin of an edge (probability ~1e-3 per row end) takes
+// the reference's exact test (cover_exact, bit-identical decision), so the set of fragments is the forward's.
+// Faces without usable bounds (zero area, NaN, huge, two near-horizontal edges) and knife-edge rows on a
+// near-horizontal edge test every bounding-box pixel exactly.
+// ------------------------------------------------------------------------------------------
+constexpr int PREFIX_STRIDE = TILE + 1;
+// The prefix sums are kept in float64: a span sum is a DIFFERENCE of two prefixes, and with fp32 prefixes its
+// error would be an ulp of the whole row's running sum (measured: 2e-4 relative on grad_p6, the moments then
+// cancel against each other) instead of an ulp of the span sum.  2 x 16 x 17 doubles = 4352 B: exactly the
+// forward-only part of WarpSmem (slot + span + hit masks), which the backward modes do not use.
+__device__ __forceinline__ double* prefix_e0(WarpSmem& S) { return reinterpret_cast<double*>(S.slot); }
+static_assert(offsetof(WarpSmem, qface) >= 2 * TILE * PREFIX_STRIDE * sizeof(double), "prefix arrays overlay slot + span + hit masks");
+
+// per-warp shared memory of the replay-only residual/backward kernel (k_step_replay): nothing of the forward's state
+struct __align__(16) ReplayWarpSmem {
+    double pre[2 * TILE * PREFIX_STRIDE];   // E0 | E1
+    float  acc[TILE_PIX];                   // g (0 where no gradient)
+    int    landing[2][36];                  // the next two batch records in flight (cp.async): {next, count, 32 face ids}
+    int    qface[32];                       // faces of the current batch
+};
+__device__ __forceinline__ double* prefix_e0(ReplayWarpSmem& S) { return S.pre; }
+
+// exclusive prefix sums of g (S.acc) and g*x' (x' = tile-relative column) along the 16 rows of the tile;
+// lane = (row, half row)
+template <class WS>
+__device__ __forceinline__ void build_row_prefix(WS& S, int lane) {
+    const int row = lane >> 1, half = lane & 1;
+    const float4 a = *reinterpret_cast<const float4*>(S.acc + row * TILE + half * 8);
+    const float4 b = *reinterpret_cast<const float4*>(S.acc + row * TILE + half * 8 + 4);
+    const float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    double e0[8], e1[8], p0 = 0.0, p1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        e0[k] = p0; e1[k] = p1;
+        p0 += (double)g[k];
+        p1 = fma((double)g[k], (double)(half * 8 + k), p1);
+    }
+    const double t0 = __shfl_sync(FULL, p0, lane & ~1), t1 = __shfl_sync(FULL, p1, lane & ~1);
+    const double o0 = half ? t0 : 0.0, o1 = half ? t1 : 0.0;
+    __syncwarp();                                       // the overlay may still be read as forward state by a slower lane
+    double* E0 = prefix_e0(S) + row * PREFIX_STRIDE + half * 8;
+    double* E1 = E0 + TILE * PREFIX_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { E0[k] = e0[k] + o0; E1[k] = e1[k] + o1; }
+    if (half) { E0[8] = p0 + o0; E1[8] = p1 + o1; }
+    __syncwarp();
+}
+
+struct SpanSetupB {
+    SpanSetup sp;        // bounds widened outward by the face's margin
+    float din;           // lo + din <= x <= hi - din: certainly covered
+    unsigned doubt;      // bit r: row r of the face's rows in this tile takes the exact test on its whole bounding-box
+                         // row — all rows of a face without usable bounds (zero area, NaN, huge, two near-horizontal
+                         // edges); the first / last row when it lies within rounding of a near-horizontal edge
+};
+
+// t_first / t_last: y - ay of the first and last row of the face in this tile (nrows rows); smax: max |x - ax|
+__device__ __forceinline__ SpanSetupB span_setup_bwd(const EdgeSetup& es, float t_first, float t_last, int nrows, float smax) {
+    SpanSetupB B;
+    B.sp = {0.0f, -3.0e38f, 0.0f, -3.0e38f, 0.0f, 3.0e38f, 0.0f, 3.0e38f};
+    const float tmax = fmaxf(fabsf(t_first), fabsf(t_last));
+    float fb = 0.0f, fg = 1.0f, fthr = 0.0f;     // near-horizontal edge: value fb*t + fg on row t, decided when |value| > fthr
+    const float sg = es.k3 < 0.0f ? -1.0f : 1.0f;
+    const float a[3] = {sg * es.q, -sg * es.p, -sg * (es.q - es.p)};
+    const float beta[3] = {-sg * es.n, sg * es.m, -sg * (es.m - es.n)};
+    const float gamma[3] = {0.0f, 0.0f, fabsf(es.k3)};
+    bool have_l = false, have_u = false;
+    float mmax = 0.0f;
+    int nflat = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const bool use = fabsf(a[j]) > 1e-4f;
+        const float ia = use ? __fdividef(1.0f, a[j]) : 0.0f;
+        const float R = -beta[j] * ia, C = -gamma[j] * ia;
+        const float margin = 1e-4f + 8e-6f * (fabsf(C) + fabsf(R) * tmax) + 1e-6f * fabsf(es.ax);
+        const bool lower = use && a[j] > 0.0f, upper = use && a[j] < 0.0f;
+        const float cl = es.ax + C - margin, cu = es.ax + C + margin;
+        if (lower && !have_l) { B.sp.RL0 = R; B.sp.CL0 = cl; } else if (lower) { B.sp.RL1 = R; B.sp.CL1 = cl; }
+        if (upper && !have_u) { B.sp.RU0 = R; B.sp.CU0 = cu; } else if (upper) { B.sp.RU1 = R; B.sp.CU1 = cu; }
+        have_l |= lower; have_u |= upper;
+        if (use) mmax = fmaxf(mmax, margin);
+        else {
+            ++nflat;
+            fb = beta[j]; fg = gamma[j];
+            fthr = fabsf(a[j]) * smax + 1e-5f * (fabsf(beta[j]) * tmax + fabsf(gamma[j])) + 1e-30f;
+        }
+    }
+    B.din = 2.0f * mmax;
+    // A near-horizontal edge is the top or the bottom of the triangle, so the rows of the bounding box lie on its
+    // inner side; only the first or the last row can come within rounding of it (the value is linear in t).
+    const float ak3 = fabsf(es.k3);
+    const bool exactall = !((ak3 > 1e-6f) && (ak3 < 1e10f)) || nflat > 1;   // NaN coordinates: every `use` is false
+    B.doubt = exactall ? 0xffffu : 0u;
+    if (!(fmaf(fb, t_first, fg) > fthr)) B.doubt |= 1u;
+    if (!(fmaf(fb, t_last, fg) > fthr)) B.doubt |= 1u << ((nrows - 1) & 15);
+    return B;
+}
+
+// rare path of one (face, row): columns outside [xsi, xei] (all of them when that range is empty) take the
+// reference's exact test.  Few scalars in, one float4 out: sum g, sum g*k1, sum g*k2 with k1, k2 evaluated per pixel
+// exactly as the forward does (a zero-area face has k1 = k2 = 0 on every pixel it covers, so its moments — and with
+// them its gradients, before the 1/(k3^2 + eps) factor — are exact zeros like the reference's), and the fragment
+// count.  The face is re-read from its p6 row; nothing of the caller's state has its address taken.
+// grow = the tile row of g (16 floats); xs/xe/xsi/xei tile-relative columns; y absolute.
+__device__ __noinline__ float4 bwd_row_exact(const float* __restrict__ p6row, const float* grow,
+                                             int xs, int xe, int xsi, int xei, int tx0, int y) {
+    const EdgeSetup es = edge_setup(__ldg(p6row), __ldg(p6row + 1), __ldg(p6row + 2), __ldg(p6row + 3), __ldg(p6row + 4), __ldg(p6row + 5));
+    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
+    int cnt = 0;
+    for (int x = xs; x <= xe; ++x) {
+        float s, t, k1, k2, w0, w1, w2;
+        bool in = (x >= xsi) & (x <= xei);
+        if (!in) {
+            in = cover_exact<false>(es, (float)(tx0 + x), (float)y, s, t, k1, k2, w0, w1, w2);
+        } else {
+            s = __fsub_rn((float)(tx0 + x), es.ax); t = __fsub_rn((float)y, es.ay);
+            k1 = __fmaf_rn(s, es.q, -__fmul_rn(es.n, t));
+            k2 = __fmaf_rn(es.m, t, -__fmul_rn(s, es.p));
+        }
+        if (in) {
+            const float g = grow[x];
+            M0 += g; A1 = fmaf(g, k1, A1); A2 = fmaf(g, k2, A2);
+            ++cnt;
+        }
+    }
+    return make_float4(M0, A1, A2, __int_as_float(cnt));
+}
+
+template <class ThreadStats, class WS>
+__device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S, float* gmus,
+                                                   int b, int nb, int tx0, int ty0, int tx1, int ty1,
+                                                   int lane, ThreadStats& st) {
+    const bool queued = lane < nb;
+    const int f = queued ? S.qface[lane] : 0;
+    const long long bf = (long long)b * P.F + f;
+    const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
+    float M0 = 0.0f, Ss = 0.0f, St = 0.0f;              // sum g, sum g*(x - ax), sum g*(y - ay) over the face's fragments
+    float A1x = 0.0f, A2x = 0.0f;                       // sum g*k1, sum g*k2 of the rows that took the exact path
+    typename ThreadStats::count_t nfrag{};
+    {
+        // Only what the row loop needs stays live in it (the kernel runs at the 64-register cap): the edge
+        // constants, lengths, labels and facing sign are (re)loaded afterwards — L1 hits — for the epilogue.
+        int cx0 = 0, cy0 = 0, bw = 1, bh = 0;
+        float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
+        if (queued) {
+            const short4 fb = __ldg(P.face_box + bf);
+            const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+            ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+            cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
+            bw = min((int)fb.z, tx1) - cx0 + 1;
+            bh = min((int)fb.w, ty1) - cy0 + 1;
+            prefetch_l1(P.len3 + bf * 3);               // the epilogue's operands travel while the rows are walked
+            prefetch_l1(P.ff + bf);
+        }
+        __syncwarp();                                   // queue entries consumed
+        if (lane == 0) st.visits++;
+        const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+        const int x_hi = cx0 + bw - 1;
+        const SpanSetupB sb = span_setup_bwd(es, (float)cy0 - es.ay, (float)(cy0 + bh - 1) - es.ay, bh,
+                                             fmaxf(fabsf((float)cx0 - es.ax), fabsf((float)x_hi - es.ax)));
+        // everything below in tile-relative coordinates (columns 0..15, rows 0..15)
+        const float axr = es.ax - (float)tx0;
+        const double axd = (double)axr;
+        const float xlo = (float)(cx0 - tx0), xhi = (float)(x_hi - tx0);
+        const float cl0 = sb.sp.CL0 - (float)tx0, cl1 = sb.sp.CL1 - (float)tx0;
+        const float cu0 = sb.sp.CU0 - (float)tx0, cu1 = sb.sp.CU1 - (float)tx0;
+        const double* E0 = prefix_e0(S);
+        const int bhmax = __reduce_max_sync(FULL, bh);
+        const float t0 = (float)cy0 - es.ay;            // y - ay of the face's first row in this tile
+        const int rowbase0 = (cy0 - ty0) * PREFIX_STRIDE;
+        unsigned exact_rows = 0u;                       // rows left to the exact path below (kept out of the hot loop:
+                                                        // a call inside it would force spills around every iteration)
+        {
+            float t = t0;
+            int rowbase = rowbase0;
+#pragma unroll 1
+            for (int r = 0; r < bhmax; ++r, t += 1.0f, rowbase += PREFIX_STRIDE) {
+                if (r < bh) {
+                    const float lo = fmaxf(fmaf(sb.sp.RL0, t, cl0), fmaf(sb.sp.RL1, t, cl1));
+                    const float hi = fminf(fmaf(sb.sp.RU0, t, cu0), fmaf(sb.sp.RU1, t, cu1));
+                    const float fs = ceilf(fmaxf(lo, xlo)), fe = floorf(fminf(hi, xhi));   // candidate columns of this row
+                    // the reference's exact test must decide: the row ends when a pixel centre lies within the margin
+                    // of an edge; the whole bounding-box row when the row is in doubt (see SpanSetupB::doubt)
+                    if (((sb.doubt >> r) & 1u) | (fs - lo < sb.din) | (hi - fe < sb.din)) {
+                        exact_rows |= 1u << r;
+                    } else if (fs <= fe) {
+                        const int xs = (int)fs, xe = (int)fe;
+                        const double* q0 = E0 + rowbase + xs;
+                        const double* q1 = E0 + rowbase + xe + 1;
+                        const double d0 = q1[0] - q0[0];
+                        const double d1 = (q1[TILE * PREFIX_STRIDE] - q0[TILE * PREFIX_STRIDE]) - axd * d0;     // sum g*(x' - ax')
+                        const float s0 = (float)d0;
+                        M0 += s0; Ss += (float)d1; St = fmaf(t, s0, St);
+                        nfrag += (unsigned)(xe - xs + 1);
+                    }
+                }
+            }
+        }
+        if (__any_sync(FULL, exact_rows != 0u)) {       // about one batch in five has such a row
+#pragma unroll 1
+            while (exact_rows) {
+                const int r = __ffs(exact_rows) - 1;
+                exact_rows &= exact_rows - 1u;
+                const float t = t0 + (float)r;
+                const bool doubt = (sb.doubt >> r) & 1u;
+                const float lo = fmaxf(fmaf(sb.sp.RL0, t, cl0), fmaf(sb.sp.RL1, t, cl1));
+                const float hi = fminf(fmaf(sb.sp.RU0, t, cu0), fmaf(sb.sp.RU1, t, cu1));
+                const float fs = doubt ? xlo : ceilf(fmaxf(lo, xlo)), fe = doubt ? xhi : floorf(fminf(hi, xhi));
+                if (fs <= fe) {
+                    // certain columns: [ceil(lo + din), floor(hi - din)], none when the row is in doubt
+                    const int xsi = doubt ? 32 : __float2int_ru(lo + sb.din), xei = doubt ? -1 : __float2int_rd(hi - sb.din);
+                    const int ry = cy0 - ty0 + r;
+                    const float4 e = bwd_row_exact(reinterpret_cast<const float*>(pp), S.acc + ry * TILE, (int)fs, (int)fe, xsi, xei, tx0, ty0 + ry);
+                    M0 += e.x; A1x += e.y; A2x += e.z; nfrag += (unsigned)__float_as_int(e.w);
+                }
+            }
+        }
+    }
+    st.cand += nfrag; st.frag += nfrag;
+    if (queued && (M0 != 0.0f || Ss != 0.0f || St != 0.0f || A1x != 0.0f || A2x != 0.0f)) {
+        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+        const EdgeSetup es = edge_setup(va.x, va.y, vb.x, vb.y, vc.x, vc.y);
+        const int2 lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
+        const float* pl = P.len3 + bf * 3;
+        const float r0 = __ldg(pl), r1 = __ldg(pl + 1), r2 = __ldg(pl + 2);
+        float sgn = (__ldg(P.ff + bf) < 0.0f) ? -1.0f : 1.0f;         // diff_fp_for.cu:94-96
+        if (lab.x == lab.y) sgn = -sgn;                               // :167-169
+        // the k1 / k2 moments from sum g*(x - ax), sum g*(y - ay)  (k1 = q*s - n*t, k2 = m*t - p*s)
+        const float A1 = fmaf(es.q, Ss, -(es.n * St)) + A1x, A2 = fmaf(es.m, St, -(es.p * Ss)) + A2x;
+        const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
+        const float cgeo = sgn * (mu_in - mu_out);                    // raw mu, no label-0 flip (back.cu:115)
+        float gp[6], gl[3], bsum;
+        face_grads_from_moments(es, r0, r1, r2, cgeo, M0, A1, A2, gp, gl, bsum);
+        float* dl = P.grad_len3 + bf * 3;                             // back.cu:126-136
+        atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
+        // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
+        st.mus_add(gmus, lab.x, (lab.x == 0 ? -sgn : sgn) * bsum, lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
+        float* dp = P.grad_p6 + bf * 6;                               // back.cu:285-292
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
 // tile load / store helpers (one warp, 16x16 pixels, rows of 64 B)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -1119,6 +1376,164 @@ __device__ __forceinline__ void tile_load(T* dst_smem, const T* __restrict__ src
         T v = fill;
         if (ty0 + row <= ty1 && tx0 + col <= tx1) v = src[base + (long long)(ty0 + row) * W + tx0 + col];
         dst_smem[row * TILE + col] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual/backward sweep of the residual step, replay only: one CTA per (angle, region) like k_raster, but all
+// it needs is what the forward sweep recorded — per tile the chain of face batches (RasterParams::brec).  No region
+// lists, no chunk walk, no face queue, none of the forward's shared memory: a small kernel whose registers go to
+// the row loop of process_batch_rows.  Regions the forward could not record (bflag 0) are left to
+// k_raster<MODE_STEP> launched right after it, which skips the recorded ones.
+// ------------------------------------------------------------------------------------------
+struct ReplayCtaSmem {
+    int next_tile;
+    ReplayWarpSmem warp[WARPS];
+};
+
+__device__ __forceinline__ void prefetch_record(const RasterParams& P, int* L, int off, int lane) {
+    const int* r = P.brec + (long long)off * BREC_INTS;
+    cp_async4(L + 2 + lane, r + 2 + lane);
+    if (lane < 2) cp_async4(L + lane, r + lane);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(THREADS, 8)
+k_step_replay(const RasterParams P) {
+    __shared__ ReplayCtaSmem C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* gmus = reinterpret_cast<float*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int regions = P.regions_x * P.regions_y;
+    const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
+    const int rr = P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions);
+    const int bflag = (int)P.bflag[(long long)b * regions + rr];
+    if (bflag == 0) return;                                   // not recorded: k_raster<MODE_STEP> walks this region
+    const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
+    const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
+    ReplayWarpSmem& S = C.warp[warp];
+    ThreadStatsT<STATS> st;
+    double loss_acc = 0.0;
+    unsigned nvalid_acc = 0u;
+    for (int k = tid; k < P.n_mus; k += THREADS) gmus[k] = 0.0f;
+    if (tid == 0) C.next_tile = 0;
+    __syncthreads();
+    const long long base = (long long)b * P.H * P.W;
+    if (bflag == 2) {
+        // nothing projects into this region: phat == 0 everywhere, residual = -target, no gradient
+        if (0.0f <= P.mask_hi) {
+            const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
+            const bool vec = ((P.W & 3) == 0) && ((rw & 3) == 0);
+            if (vec) {
+                // a pure stream of the target: several rows per lane in flight (float4 = four pixels)
+                const int rw4 = rw >> 2, n4 = rw4 * rh;
+                const float* org = P.target + base + (long long)ry0 * P.W + rx0;
+#pragma unroll 4
+                for (int k = tid; k < n4; k += THREADS) {
+                    const int y = k / rw4, x = (k - y * rw4) * 4;
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(org + (long long)y * P.W + x));
+                    loss_acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
+                }
+            } else {
+                for (int y = warp; y < rh; y += WARPS) {
+                    const float* row = P.target + base + (long long)(ry0 + y) * P.W + rx0;
+                    for (int x = lane; x < rw; x += 32) { const float t = __ldg(row + x); loss_acc += (double)t * (double)t; }
+                }
+            }
+            if (tid == 0) nvalid_acc += (unsigned)(rw * rh);
+        }
+    } else {
+        const int tiles_x = (P.W + TILE - 1) / TILE, tiles_y = (P.H + TILE - 1) / TILE;
+        const int ntiles = P.RT * P.RT;
+        while (true) {
+            int tix = 0;
+            if (lane == 0) tix = atomicAdd(&C.next_tile, 1);
+            tix = __shfl_sync(FULL, tix, 0);
+            if (tix >= ntiles) break;
+            const int tx0 = rx0 + (tix % P.RT) * TILE, ty0 = ry0 + (tix / P.RT) * TILE;
+            if (tx0 > rx1 || ty0 > ry1) continue;
+            const int tx1 = min(tx0 + TILE - 1, rx1), ty1 = min(ty0 + TILE - 1, ry1);
+            const int roff0 = __ldg(P.bhead + ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4));
+            if (roff0 >= 0) prefetch_record(P, S.landing[0], roff0, lane);  // in flight during the tile prologue
+            // residual prologue: g = d/dphat of sum_valid (target - phat)^2 = 2*(phat - target) on pixels passing
+            // get_valid_mask (fp_vecs.py:10-13; a subset of the kernel's own gradient predicate,
+            // diff_fp_for.cu:69-73); loss and count once per tile
+            const int col = lane & 15, r = lane >> 4;
+            float vv[TILE / 2], tt[TILE / 2];
+#pragma unroll
+            for (int k = 0; k < TILE / 2; ++k) {              // all 16 loads in flight before any use
+                const int row = r + 2 * k;
+                const bool ok = (ty0 + row <= ty1) && (tx0 + col <= tx1);
+                const long long o = base + (long long)(ty0 + row) * P.W + tx0 + col;
+                vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
+                tt[k] = ok ? __ldg(P.target + o) : 0.0f;
+            }
+            // Record pipeline: while batch k is processed, record k+1 has landed (its faces' data is being pulled
+            // into L2 by prefetches) and record k+2 is in flight.  `cur` holds batch k's faces.
+            int nbatch = 0, next = -1, id = 0, slot = 0;
+            if (roff0 >= 0) {
+                cp_async_wait_all();
+                __syncwarp();
+                const int* L0 = S.landing[0];
+                next = L0[0]; nbatch = L0[1]; id = L0[2 + lane];
+                if (next >= 0) prefetch_record(P, S.landing[1], next, lane);
+                slot = 1;
+                if (lane < nbatch) {                          // the first batch's face data: on its way during the g / prefix work
+                    const long long bf = (long long)b * P.F + id;
+                    prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
+                    prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TILE / 2; ++k) {
+                float g = 0.0f;
+                if (vv[k] > -1e-6f && vv[k] <= P.mask_hi) {
+                    const float diff = vv[k] - tt[k];
+                    g = 2.0f * diff;
+                    loss_acc += (double)diff * (double)diff; nvalid_acc++;
+                }
+                S.acc[(r + 2 * k) * TILE + col] = g;
+            }
+            __syncwarp();
+            if (roff0 < 0) continue;                                  // no face reaches this tile
+            build_row_prefix(S, lane);
+            while (true) {
+                if (lane < nbatch) S.qface[lane] = id;
+                const int nb_cur = nbatch;
+                const bool more = next >= 0;
+                if (more) {
+                    // record k+1 has landed: read it, prefetch its faces' data towards L2, start record k+2
+                    cp_async_wait_all();
+                    __syncwarp();
+                    const int* L = S.landing[slot];
+                    next = L[0]; nbatch = L[1]; id = L[2 + lane];
+                    slot ^= 1;
+                    if (next >= 0) prefetch_record(P, S.landing[slot], next, lane);
+                    if (lane < nbatch) {
+                        const long long bf = (long long)b * P.F + id;
+                        prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
+                        prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
+                    }
+                }
+                __syncwarp();
+                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
+                if (!more) break;
+            }
+        }
+    }
+    st.mus_flush(gmus);
+    __syncthreads();
+    for (int k = tid; k < P.n_mus; k += THREADS) {
+        const float v = gmus[k];
+        if (v != 0.0f) atomicAdd(P.grad_mus + k, v);
+    }
+    // masked L2 data term of ctdr/optimize.py:168: sum over valid pixels and their count
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) loss_acc += __shfl_down_sync(FULL, loss_acc, d);
+    nvalid_acc = __reduce_add_sync(FULL, nvalid_acc);
+    if (lane == 0) {
+        if (loss_acc != 0.0) atomicAdd(P.out2 + 0, loss_acc);
+        if (nvalid_acc) atomicAdd(P.out2 + 1, (double)nvalid_acc);
     }
 }
 
@@ -1377,6 +1792,7 @@ k_raster(const RasterParams P) {
             int qn = 0, lb = 0, cid = 0;
             unsigned m = 0u;
             bool exhausted = false;
+            bool prefix_ready = false;                      // backward: row prefix sums of g, built at the tile's first batch
             const short4* fbrow = P.face_box + (long long)b * P.F;
             while (true) {
                 int nbatch;
@@ -1457,7 +1873,10 @@ k_raster(const RasterParams P) {
                 }
                 }
                 if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
-                else process_batch_blocked<MODE, EXACT_DIV, DIRECT>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                else if (K_BWD) {
+                    if (!prefix_ready) { build_row_prefix(S, lane); prefix_ready = true; }
+                    process_batch_rows(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                } else process_batch_blocked<MODE, EXACT_DIV, DIRECT>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
                 if (!replay) {
                     const int rest = qn - nbatch;              // < 32: shift the tail to the front
                     int tf = 0;

@@ -15,6 +15,7 @@ struct VertexParams {
     int kind;
     const float* geom;            // angles[nangles] or Vectors[nangles,12]
     const long long* idx_angles;  // [B]
+    int nangles;                  // rows of `geom`; an index outside [0, nangles) poisons its angle with NaN
     int B, V, F, H, W;
     const float* verts;           // [V,3]
     const int* faces;             // [F,3]
@@ -33,6 +34,13 @@ struct AngleConst {
 __device__ __forceinline__ AngleConst angle_const(const VertexParams& P, int b) {
     AngleConst A = {};
     const long long row = P.idx_angles[b];
+    if ((unsigned long long)row >= (unsigned long long)P.nangles) {
+        // the reference raises IndexError (self.vecs[idx_angles], fp_vecs.py:101); a kernel cannot, so the
+        // angle's output becomes NaN instead of reading outside the geometry table (hosts validate beforehand)
+        const float nan = __int_as_float(0x7fc00000);
+        A.ct = A.st = A.Sx = A.Sy = A.Sz = A.N0 = A.N1 = A.ux = A.uy = A.vz = A.DSx = A.DSy = A.DSz = A.coeff = nan;
+        return A;
+    }
     if (P.kind == 0) {
         const float th = __ldg(P.geom + row);
         A.ct = cosf(th); A.st = sinf(th);                               // fp_opengl.py:89-90

@@ -49,24 +49,54 @@ def shard_angles(nangles: int, rank: int, world: int) -> tuple[int, int]:
 class GradientExchange:
     """Flat, pre-allocated all-reduce buffers the backward writes into directly (no pack kernel).
 
-    ``flat`` (fp32) = [grad_verts (3V) | grad_mus (n)], ``scalars`` (fp64) = [loss_sum, n_valid].
+    ``flat`` (fp32) = [grad_verts (3V) | grad_mus (n)], ``scalars`` (fp64) = [loss_sum, n_valid].  Both are views
+    of ONE byte buffer, so a single fill zeroes them, and the two all-reduces (different dtypes) are issued as
+    one NCCL group (one launch) behind the backward kernels on the current stream.
     """
 
     def __init__(self, num_verts: int, num_mus: int, device):
-        self.flat = torch.zeros(3 * num_verts + num_mus, dtype=torch.float32, device=device)
+        nflat = 3 * num_verts + num_mus
+        off = (4 * nflat + 15) // 16 * 16                     # fp64 pair behind the fp32 part, 16-byte aligned
+        self.storage = torch.zeros(off + 16, dtype=torch.uint8, device=device)
+        self.flat = self.storage[:4 * nflat].view(torch.float32)
         self.grad_verts = self.flat[:3 * num_verts].view(num_verts, 3)
         self.grad_mus = self.flat[3 * num_verts:]
-        self.scalars = torch.zeros(2, dtype=torch.float64, device=device)
+        self.scalars = self.storage[off:off + 16].view(torch.float64)
 
     def zero_(self):
-        self.flat.zero_()
-        self.scalars.zero_()
+        self.storage.zero_()
+
+    @staticmethod
+    def _active() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def all_reduce_tensors(self, flat, scalars):
+        """SUM over ranks of an fp32 buffer and an fp64 pair as one grouped launch where the backend can."""
+        if not self._active():
+            return
+        manager = getattr(dist, "_coalescing_manager", None)
+        if manager is not None and dist.get_backend() == "nccl":
+            try:
+                with manager(device=flat.device):
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                    dist.all_reduce(scalars, op=dist.ReduceOp.SUM)
+                return
+            except (TypeError, RuntimeError):                 # API drift between torch versions: two plain calls
+                pass
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        dist.all_reduce(scalars, op=dist.ReduceOp.SUM)
 
     def all_reduce(self):
         """Sum over ranks, enqueued on the current stream right behind the backward kernels."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.scalars, op=dist.ReduceOp.SUM)
+        self.all_reduce_tensors(self.flat, self.scalars)
+
+    @staticmethod
+    def kernels_per_exchange(world: int) -> int:
+        """Kernels one zero_() + all_reduce() enqueues besides the library's own (for launch accounting)."""
+        return 1 + (1 if world > 1 else 0)
+
+    def loss_sum_and_count(self):
+        return tuple(float(x) for x in self.scalars.tolist())
 
     def mean_gradients(self):
         """d(mean over valid pixels)/d(verts, mus) and the mean loss, from the all-reduced sums."""

@@ -132,22 +132,26 @@ class GeometryDevice:
         self.nangles = int(self.table.shape[0])
 
 
-_adjacency_cache: dict = {}
+_adjacency_cache: dict = {}       # (data_ptr, F, version, V) -> (faces tensor kept alive, start, corner); a few meshes
 
 
 def vertex_adjacency(faces_i32, num_verts):
     """CSR vertex -> incident face corners (3*face + corner), grouped by vertex in ascending corner
-    order (stable sort): what the deterministic backward gathers over.  Cached per faces tensor."""
-    hit = _adjacency_cache.get("entry")
-    if hit is None or hit[0] is not faces_i32 or hit[1] != int(num_verts) or hit[2] != faces_i32._version:
+    order (stable sort): what the deterministic backward gathers over.  Cached per faces tensor
+    (several meshes may alternate: coarse-to-fine stages, config-5 style batches)."""
+    key = (faces_i32.data_ptr(), int(faces_i32.shape[0]), faces_i32._version, int(num_verts))
+    hit = _adjacency_cache.get(key)
+    if hit is None:
         flat = faces_i32.reshape(-1).to(torch.int64)
         order = torch.sort(flat, stable=True).indices.to(torch.int32).contiguous()
         counts = torch.bincount(flat, minlength=int(num_verts))
         start = torch.zeros(int(num_verts) + 1, dtype=torch.int32, device=faces_i32.device)
         start[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        hit = (faces_i32, int(num_verts), faces_i32._version, start.contiguous(), order)
-        _adjacency_cache["entry"] = hit
-    return hit[3], hit[4]
+        if len(_adjacency_cache) >= 8:
+            _adjacency_cache.pop(next(iter(_adjacency_cache)))
+        hit = (faces_i32, start.contiguous(), order)       # keeping the faces tensor alive pins its data_ptr
+        _adjacency_cache[key] = hit
+    return hit[1], hit[2]
 
 
 def _adjacency_ptrs(flags, faces_i32, num_verts):
@@ -157,15 +161,42 @@ def _adjacency_ptrs(flags, faces_i32, num_verts):
     return None, None
 
 
-def _device_idx(idx_angles, device):
-    return torch.as_tensor(idx_angles).to(device=device, dtype=torch.int64).contiguous()
+def _device_idx(idx_angles, device, nangles=None):
+    """int64 angle indices on the device.  Host indices are range-checked first (the reference raises IndexError
+    through ``self.vecs[idx_angles]``, fp_vecs.py:101); device tensors are not (no sync) — an out-of-range row
+    there turns that angle's output into NaN (ctdr_vertex.cuh::angle_const)."""
+    t = torch.as_tensor(idx_angles)
+    if nangles is not None and not t.is_cuda and t.numel():
+        lo, hi = int(t.min()), int(t.max())
+        if lo < -nangles or hi >= nangles:
+            raise IndexError(f"angle index out of range for a geometry with {nangles} angles: [{lo}, {hi}]")
+        if lo < 0:
+            t = torch.where(t < 0, t + nangles, t)          # negative indices like torch indexing
+    return t.to(device=device, dtype=torch.int64).contiguous()
+
+
+def _check_mesh(geom, verts, faces_i32, labels, mus, idx):
+    """Device, dtype, contiguity and shape of everything the fused entry points hand to the C ABI (which only
+    checks for NULL): returns the contiguous tensors."""
+    verts = _lib.require_cuda_f32(verts, "verts_vx3")
+    mus = _lib.require_cuda_f32(mus, "mus_n")
+    faces_i32 = _lib.require_cuda_i32(faces_i32, "faces_fx3")
+    labels = _lib.require_cuda_i32(labels, "labels_fx2")
+    if verts.dim() != 2 or verts.shape[1] != 3 or faces_i32.dim() != 2 or faces_i32.shape[1] != 3:
+        raise RuntimeError("verts must be [V,3] and faces [F,3]")
+    if labels.shape != (faces_i32.shape[0], 2):
+        raise RuntimeError("labels_fx2 must be [F,2]")
+    if not idx.is_cuda or idx.dtype != torch.int64:
+        raise RuntimeError("idx_angles must be a CUDA int64 tensor here (use _device_idx)")
+    return verts, faces_i32, labels, mus, idx.contiguous()
 
 
 def vertex_forward(geom: GeometryDevice, verts, faces_i32, idx_angles):
     """p_bxfx6, len_bxfx3, front_facing_bxfx1 exactly as the reference FP modules build them."""
     verts = _lib.require_cuda_f32(verts, "verts_vx3")
+    faces_i32 = _lib.require_cuda_i32(faces_i32, "faces_fx3")
     dev = verts.device
-    idx = _device_idx(idx_angles, dev)
+    idx = _device_idx(idx_angles, dev, geom.nangles)
     B, V, F = idx.numel(), verts.shape[0], faces_i32.shape[0]
     p6 = torch.empty(B, F, 6, dtype=torch.float32, device=dev)
     len3 = torch.empty(B, F, 3, dtype=torch.float32, device=dev)
@@ -186,7 +217,7 @@ class VertexStage(Function):
     def forward(ctx, verts, faces_i32, idx_angles, geom):
         p6, len3, ff = vertex_forward(geom, verts, faces_i32, idx_angles)
         ctx.geom = geom
-        ctx.save_for_backward(verts.contiguous(), faces_i32, _device_idx(idx_angles, verts.device))
+        ctx.save_for_backward(verts.contiguous(), faces_i32, _device_idx(idx_angles, verts.device, geom.nangles))
         ctx.mark_non_differentiable(ff)                            # rasterizer.py:107: no gradient
         return p6, len3, ff
 
@@ -210,13 +241,14 @@ class VertexStage(Function):
 
 def project_forward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, *, want_cnt=False, want_stats=False,
                     flags=None, need_backward=False):
+    verts, faces_i32, labels, mus, idx = _check_mesh(geom, verts, faces_i32, labels, mus, idx)
     dev = verts.device
     B, V, F = idx.numel(), verts.shape[0], faces_i32.shape[0]
     im = torch.empty(B, geom.H, geom.W, dtype=torch.float32, device=dev)
     cnt = torch.empty(B, geom.H, geom.W, dtype=dtype_int, device=dev) if want_cnt else None
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
-    ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, int(need_backward)))
+    ws = _lib.workspace(dev, _lib.project_workspace_bytes(B, V, F, geom.H, geom.W, need_backward))
     with torch.cuda.device(dev):
         rc = L.ctdr_project_forward(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                     verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(), mus.data_ptr(),
@@ -253,7 +285,8 @@ def raster_forward_multi(p6, len3, ff, labels, mus_kxn, H, W, max_sino_val, *, t
     want_gram = want_gram or target is not None
     gram = torch.empty(K * K + K, dtype=torch.float64, device=dev) if want_gram else None
     if target is not None:
-        target = _lib.require_cuda_f32(target, "target")
+        target = _lib.require_numel(_lib.require_cuda_f32(target, "target"), B * H * W, "target")
+    labels = _lib.require_cuda_i32(labels, "labels_fx2")
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
     ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
@@ -272,8 +305,9 @@ def project_forward_multi(geom: GeometryDevice, verts, faces_i32, labels, mus_kx
                           want_gram=False, want_stats=False, flags=None):
     """Fused projector, ``K`` attenuation vectors in one sweep (``ctdr_project_forward_multi``); see
     :func:`raster_forward_multi` for the outputs."""
-    dev = verts.device
     mus_kxn = _lib.require_cuda_f32(mus_kxn, "mus_kxn")
+    verts, faces_i32, labels, _, idx = _check_mesh(geom, verts, faces_i32, labels, mus_kxn.reshape(-1), idx)
+    dev = verts.device
     B, V, F, K = idx.numel(), verts.shape[0], faces_i32.shape[0], mus_kxn.shape[0]
     im = torch.empty(K, B, geom.H, geom.W, dtype=torch.float32, device=dev)
     want_gram = want_gram or target is not None
@@ -284,7 +318,7 @@ def project_forward_multi(geom: GeometryDevice, verts, faces_i32, labels, mus_kx
             raise RuntimeError("target must hold B*H*W values")
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
-    ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 0))
+    ws = _lib.workspace(dev, _lib.project_workspace_bytes(B, V, F, geom.H, geom.W, False))
     with torch.cuda.device(dev):
         rc = L.ctdr_project_forward_multi(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                           verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(),
@@ -299,16 +333,18 @@ def project_forward_multi(geom: GeometryDevice, verts, faces_i32, labels, mus_kx
 
 def project_backward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, grad_im, im, *, flags=None,
                      grad_verts=None, grad_mus=None):
+    verts, faces_i32, labels, mus, idx = _check_mesh(geom, verts, faces_i32, labels, mus, idx)
     dev = verts.device
     B, V, F = idx.numel(), verts.shape[0], faces_i32.shape[0]
-    if grad_verts is None:
-        grad_verts = torch.zeros_like(verts)
-    if grad_mus is None:
-        grad_mus = torch.zeros_like(mus)
+    npix = B * geom.H * geom.W
+    grad_im = _lib.require_numel(_lib.require_cuda_f32(grad_im, "grad_im"), npix, "grad_im")
+    im = _lib.require_numel(_lib.require_cuda_f32(im, "im"), npix, "im")
+    grad_verts = torch.zeros_like(verts) if grad_verts is None else _lib.require_out(grad_verts, torch.float32, 3 * V, "grad_verts")
+    grad_mus = torch.zeros_like(mus) if grad_mus is None else _lib.require_out(grad_mus, torch.float32, mus.numel(), "grad_mus")
     L = _lib.lib()
     flags = default_flags() if flags is None else flags
     adj0, adj1 = _adjacency_ptrs(flags, faces_i32, V)
-    ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 1))
+    ws = _lib.workspace(dev, _lib.project_workspace_bytes(B, V, F, geom.H, geom.W, True))
     with torch.cuda.device(dev):
         rc = L.ctdr_project_backward(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                      verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(), mus.data_ptr(),
@@ -321,31 +357,47 @@ def project_backward(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, g
 
 
 def project_residual_step(geom: GeometryDevice, verts, faces_i32, labels, mus, idx, target, *, flags=None,
-                          phat=None, grad_verts=None, grad_mus=None, out2=None, want_stats=False):
+                          phat=None, grad_verts=None, grad_mus=None, out2=None, want_stats=False, stage_ms=None):
     """One projection + masked-L2 residual + backward sweep (``ctdr/optimize.py:162-168,190``).
 
     Returns ``(phat, grad_verts, grad_mus, out2)`` with ``out2 = [sum_valid (target-phat)^2, n_valid]``
     (float64, device) and the gradients of that *sum* (divide by ``n_valid`` for the mean).
-    Nothing synchronises with the host.
+    Nothing synchronises with the host — unless ``stage_ms`` (a dict) is given: then the profiling entry point
+    ``ctdr_project_residual_step_timed`` runs instead, synchronises, and fills ``stage_ms`` with the device
+    milliseconds of every stage (``_lib.STAGES``).
     """
+    verts, faces_i32, labels, mus, idx = _check_mesh(geom, verts, faces_i32, labels, mus, idx)
     dev = verts.device
     B, V, F = idx.numel(), verts.shape[0], faces_i32.shape[0]
-    phat = torch.empty(B, geom.H, geom.W, dtype=torch.float32, device=dev) if phat is None else phat
-    grad_verts = torch.zeros_like(verts) if grad_verts is None else grad_verts
-    grad_mus = torch.zeros_like(mus) if grad_mus is None else grad_mus
-    out2 = torch.zeros(2, dtype=torch.float64, device=dev) if out2 is None else out2
+    npix = B * geom.H * geom.W
+    # the C ABI only checks for NULL: a float64 sinogram (SinoDataset(dtype=float64)) or a short batch would be
+    # read as garbage / out of bounds by the kernels
+    target = _lib.require_numel(_lib.require_cuda_f32(target, "target sinogram (p_batch)"), npix, "target sinogram (p_batch)")
+    phat = (torch.empty(B, geom.H, geom.W, dtype=torch.float32, device=dev) if phat is None
+            else _lib.require_out(phat, torch.float32, npix, "phat"))
+    grad_verts = torch.zeros_like(verts) if grad_verts is None else _lib.require_out(grad_verts, torch.float32, 3 * V, "grad_verts")
+    grad_mus = torch.zeros_like(mus) if grad_mus is None else _lib.require_out(grad_mus, torch.float32, mus.numel(), "grad_mus")
+    out2 = torch.zeros(2, dtype=torch.float64, device=dev) if out2 is None else _lib.require_out(out2, torch.float64, 2, "out2")
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     L = _lib.lib()
     flags = default_flags() if flags is None else flags
     adj0, adj1 = _adjacency_ptrs(flags, faces_i32, V)
-    ws = _lib.workspace(dev, L.ctdr_project_workspace_bytes(B, V, F, geom.H, geom.W, 1))
+    ws = _lib.workspace(dev, _lib.project_workspace_bytes(B, V, F, geom.H, geom.W, True))
+    args = (geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
+            verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(),
+            mus.data_ptr(), mus.numel(), geom.H, geom.W, geom.spacing_x, geom.spacing_y,
+            float(geom.max_sino_val), target.data_ptr(), phat.data_ptr(),
+            grad_verts.data_ptr(), grad_mus.data_ptr(), out2.data_ptr(), adj0, adj1,
+            ws.data_ptr(), ws.numel(), _lib.ptr(stats), flags, _lib.stream_ptr(dev))
     with torch.cuda.device(dev):
-        rc = L.ctdr_project_residual_step(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
-                                          verts.data_ptr(), V, faces_i32.data_ptr(), F, labels.data_ptr(),
-                                          mus.data_ptr(), mus.numel(), geom.H, geom.W, geom.spacing_x, geom.spacing_y,
-                                          float(geom.max_sino_val), target.data_ptr(), phat.data_ptr(),
-                                          grad_verts.data_ptr(), grad_mus.data_ptr(), out2.data_ptr(), adj0, adj1,
-                                          ws.data_ptr(), ws.numel(), _lib.ptr(stats), flags, _lib.stream_ptr(dev))
+        if stage_ms is None:
+            rc = L.ctdr_project_residual_step(*args)
+        else:
+            import ctypes
+            host = (ctypes.c_float * len(_lib.STAGES))()
+            rc = L.ctdr_project_residual_step_timed(*args, ctypes.cast(host, ctypes.c_void_p))
+            for name, v in zip(_lib.STAGES, host):
+                stage_ms[name] = stage_ms.get(name, 0.0) + float(v)
     _lib.check(rc, "ctdr_project_residual_step")
     if want_stats:
         return phat, grad_verts, grad_mus, out2, stats
@@ -415,7 +467,7 @@ class ProjectMesh(Function):
     def forward(ctx, verts, mus, faces_i32, labels, idx_angles, geom, backprop):
         verts = _lib.require_cuda_f32(verts, "verts_vx3")
         mus = _lib.require_cuda_f32(mus, "mus_n")
-        idx = _device_idx(idx_angles, verts.device)
+        idx = _device_idx(idx_angles, verts.device, geom.nangles)
         im, _, _ = project_forward(geom, verts, faces_i32, labels, mus, idx, need_backward=bool(backprop))
         if backprop:
             ctx.geom = geom

@@ -46,6 +46,11 @@ class _ProjectorBase(nn.Module):
         self.dtype = dtype
         self.fused = fused
         self.labels_fx2 = labels.cuda().to(torch.int32).contiguous()
+        # one host sync at construction: every forward then checks mus_n against it (mus[label] is read, and in the
+        # backward written, by label; the reference would index out of bounds silently)
+        self._label_max = int(self.labels_fx2.max()) if self.labels_fx2.numel() else 0
+        if self.labels_fx2.numel() and int(self.labels_fx2.min()) < 0:
+            raise ValueError("labels must be >= 0")
         self.geom = GeometryDevice(proj_geom, self.labels_fx2.device)
         self.max_sino_val = self.geom.max_sino_val
         self.height = self.geom.H
@@ -62,6 +67,8 @@ class _ProjectorBase(nn.Module):
         return self._faces_i32
 
     def forward(self, verts_vx3, faces_fx3, idx_angles, mus_n, backprop=True):
+        if mus_n.numel() <= self._label_max:
+            raise IndexError(f"mus_n has {mus_n.numel()} entries but the face labels go up to {self._label_max}")
         faces32 = self._faces32(faces_fx3)
         if self.fused:
             im = ProjectMesh.apply(verts_vx3, mus_n, faces32, self.labels_fx2, idx_angles, self.geom, backprop)
@@ -80,7 +87,8 @@ class _ProjectorBase(nn.Module):
         ``(phat [K,B,H,W], A [K,K], rhs [K])`` with ``A[i,j] = sum phat_i*phat_j`` and
         ``rhs[i] = sum phat_i*target`` in float64 — what ``Model.estimate_mu`` (``vanilla.py:186-265``)
         obtains from 2-3 full renders plus torch reductions."""
-        idx = idx_angles.to(device=self.labels_fx2.device, dtype=torch.int64).contiguous()
+        from ..function.rasterizer import _device_idx
+        idx = _device_idx(idx_angles, self.labels_fx2.device, self.geom.nangles)
         im, A, rhs, _ = project_forward_multi(self.geom, verts_vx3.detach().contiguous(), self._faces32(faces_fx3),
                                               self.labels_fx2, mus_kxn, idx, target=target, want_gram=True)
         return im, A, rhs

@@ -27,12 +27,18 @@ def get_params(model, exclude_mus=False):
 def projection_step(model, idx_angles, p_batch, exchange=None):
     """Data term of one iteration through the fused device path.
 
-    Sets ``.grad`` of ``model.displace`` / ``model.mus`` (adding to existing gradients) to the
-    gradient of ``mean_valid (p - phat)^2`` and returns ``(data_loss, phat, n_valid)`` as device
-    tensors.  With several ranks, each passes its own angle shard and the sums are all-reduced.
+    Adds the gradient of ``mean_valid (p - phat)^2`` to ``.grad`` of every trainable parameter the displaced
+    vertices depend on — ``displace``, and ``center`` / ``scale`` when the model registers them as parameters
+    (``ctdr/model/vanilla.py:80-83,123-139``), exactly the leaves ``loss.backward()`` reaches in the reference
+    (``ctdr/optimize.py:190``) — and to ``mus.grad``; returns ``(data_loss, phat, n_valid)`` as device tensors.
+    The vertex cotangent comes out of the fused kernels; ``torch.autograd.backward`` pushes it through the few
+    torch ops of ``get_displaced_vertices``.  With several ranks, each passes its own angle shard and the sums
+    are all-reduced.
     """
     fp = model.fp
-    verts = model.get_displaced_vertices().detach().contiguous()
+    with torch.enable_grad():
+        v = model.get_displaced_vertices()
+    verts = v.detach().contiguous()
     if model.mus_fixed_no == 1:
         model.mus.data[0] = model.p_min
     mus = model.mus.detach().contiguous()
@@ -40,15 +46,16 @@ def projection_step(model, idx_angles, p_batch, exchange=None):
     if exchange is None:
         exchange = distributed.GradientExchange(verts.shape[0], mus.numel(), dev)
     exchange.zero_()
-    idx = torch.as_tensor(idx_angles).to(device=dev, dtype=torch.int64)
+    idx = R._device_idx(idx_angles, dev, fp.geom.nangles)
     phat, _, _, _ = R.project_residual_step(fp.geom, verts, fp._faces32(model.faces), fp.labels_fx2, mus, idx,
-                                            p_batch.contiguous(), grad_verts=exchange.grad_verts,
+                                            p_batch, grad_verts=exchange.grad_verts,
                                             grad_mus=exchange.grad_mus, out2=exchange.scalars)
     exchange.all_reduce()
     gverts, gmus, loss = exchange.mean_gradients()
-    for prm, g in ((model.displace, gverts), (model.mus, gmus)):
-        if isinstance(prm, torch.nn.Parameter) and prm.requires_grad:
-            prm.grad = g.clone() if prm.grad is None else prm.grad + g
+    if v.requires_grad:
+        torch.autograd.backward(v, gverts.to(v.dtype))        # -> displace.grad (+ scale.grad, center.grad)
+    if isinstance(model.mus, torch.nn.Parameter) and model.mus.requires_grad:
+        model.mus.grad = gmus.clone() if model.mus.grad is None else model.mus.grad + gmus
     return loss.to(torch.float32), phat, exchange.scalars[1]
 
 
@@ -81,8 +88,11 @@ class GraphedIteration:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
+        from . import _lib
+        launches0 = _lib.lib().ctdr_launch_count()
         with torch.cuda.graph(self.graph):
             self._iteration()
+        self.ctdr_launches_per_iteration = int(_lib.lib().ctdr_launch_count() - launches0)   # library kernels in the graph
         self.phat = self._phat
 
     def _iteration(self):
@@ -109,7 +119,12 @@ class GraphedIteration:
         return self.stats
 
 
-def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_every=60, graphed=False):
+def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_every=60, graphed=False,
+        decay_lr=False):
+    """``decay_lr``: the reference halves ``args.lr`` 100 iterations before the end of runs longer than 400
+    (``ctdr/optimize.py:148-152``) but never hands the new value to the optimiser, so its Adam step size stays
+    constant; the default reproduces exactly that (``args.lr`` changes, the optimiser does not).  ``decay_lr=True``
+    applies the halving to the optimiser as the reference apparently intended."""
     if fused is None:
         fused = getattr(model.fp, "fused", False)
     print("@ model.mus", model.mus)
@@ -134,14 +149,16 @@ def run(model, ds, niter, args, epoch_start=0, use_adam=True, fused=None, log_ev
     phat = mask_valid = None
     for epoch in range(epoch_start, niter):
         if epoch + 100 == niter and niter > 400:
-            for group in opt.param_groups:
-                group["lr"] *= 0.5
-            args.lr *= 0.5
+            args.lr *= 0.5                                  # optimize.py:150-152
             print("@ args.lr", args.lr)
+            if decay_lr:
+                for group in opt.param_groups:
+                    group["lr"] *= 0.5
+                if graph_it is not None:
+                    graph_it.set_lr(graph_it.lr.item() * 0.5)
         torch.cuda.synchronize(dev)
         start = time.time()
         if graph_it is not None:
-            graph_it.set_lr(args.lr)
             vals = graph_it.step().tolist()              # the one host sync of the iteration
             data_loss, edge_loss, lap_loss, flat_loss = (torch.tensor(v) for v in vals)
             loss = data_loss + args.wedge * edge_loss + args.wlap * lap_loss + args.wflat * flat_loss

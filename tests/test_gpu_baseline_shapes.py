@@ -50,10 +50,13 @@ def rule(name, g, g64, g32):
     return err / max(n64, 1e-300)
 
 
-def rule32(name, g, g32, rel=2e-4):
-    """Knife-edge pixels decided differently by the double instantiation: compare with the float one only."""
+def rule32(name, g, g32, rel=2e-4, cond=None):
+    """No double referee (too slow at this size): compare with the reference's float instantiation, whose own
+    float atomics carry reassociation noise.  ``cond`` = the same gradient for |cotangent| (no cancellation):
+    grad_mus is a sum over ~1e6 fragments of either sign, so its noise scales with that, not with the result."""
     err, n = float((g.double() - g32.double()).norm()), float(g32.double().norm())
-    assert err <= rel * n + 1e-30, f"{name}: |g-g32|={err:.3e} vs |g32|={n:.3e}"
+    tol = rel * n + (1e-5 * float(cond.double().norm()) if cond is not None else 0.0)
+    assert err <= tol + 1e-30, f"{name}: |g-g32|={err:.3e} > {tol:.3e} (|g32|={n:.3e})"
     return err / max(n, 1e-300)
 
 
@@ -113,27 +116,33 @@ def check_case(ref, name, angles, *, fp64=True, expect_segments=False, expect_di
         bad32 = (r32["im"].double() < -1e-5) | (r32["im"] > msv)
         bad64 = (r64["im"] < -1e-5) | (r64["im"] > msv)
         same_cover = torch.equal(r64["cnt"], r32["cnt"]) and torch.equal(bad32, bad64)
+    # With the double referee the stated rule applies as is: where the double instantiation decides a knife-edge
+    # pixel differently (same_cover False) that shows up in ||g_ref32 - g64|| and the rule loosens by itself.
     for tag, gg in (("randn", g), ("residual", g_resid)):
         g32 = ref.backward(r32, gg)
         mine = R.raster_backward(gg, r32["im"], p6, len3, ff, lab, mus, msv)
-        if same_cover:
+        if fp64:
             g64 = ref.backward(r64, gg)
+            cond = None
+        else:
+            cond = ref.backward(r32, gg.abs())[2]
         names = ("grad_p6", "grad_len3", "grad_mus")
         for k, nme in enumerate(names):
-            achieved[f"{tag}/{nme}"] = (rule(nme, mine[k], g64[k], g32[k]) if same_cover else rule32(nme, mine[k], g32[k]))
+            achieved[f"{tag}/{nme}"] = (rule(nme, mine[k], g64[k], g32[k]) if fp64
+                                        else rule32(nme, mine[k], g32[k], cond=cond if k == 2 else None))
         # ---- fused backward: grad_verts / grad_mus vs (reference raster backward) o (vertex transpose) ----
         gv32 = vertex_transpose(gd, v, f32, idx, g32[0], g32[1])
         if tag == "randn":
             gv, gm = R.project_backward(gd, v, f32, lab, mus, idx, gg.view(B, H, W).contiguous(), imf)
         else:
             gv, gm = gv_step, gm_step
-        if same_cover:
+        if fp64:
             gv64 = vertex_transpose(gd, v, f32, idx, g64[0], g64[1])
             achieved[f"{tag}/grad_verts"] = rule("grad_verts (fused)", gv, gv64, gv32)
             achieved[f"{tag}/grad_mus_fused"] = rule("grad_mus (fused)", gm, g64[2], g32[2])
         else:
             achieved[f"{tag}/grad_verts"] = rule32("grad_verts (fused)", gv, gv32)
-            achieved[f"{tag}/grad_mus_fused"] = rule32("grad_mus (fused)", gm, g32[2])
+            achieved[f"{tag}/grad_mus_fused"] = rule32("grad_mus (fused)", gm, g32[2], cond=cond)
         assert float(gv.norm()) > 0
     print(f"[{name}] B={B} F={F} {H}x{W} vf={r32['vf']} same_cover_fp64={same_cover} achieved rel. errors: "
           + ", ".join(f"{k}={e:.2e}" for k, e in achieved.items()))
@@ -190,7 +199,7 @@ def test_cfg4_pixel_offsets_beyond_int32(cuda_lib):
     for b in (0, 511, 512, 599):                       # 512 * 2048^2 = 2^31 exactly
         one, _, _ = R.project_forward(gd, v, f32, lab, mus, idx[b:b + 1].contiguous())
         assert torch.equal(one[0], im[b]), f"angle slot {b}"
-    assert float(im[599].max()) > 0.5
+    assert float(im[599].max()) > 0.4                  # the tube's chord, 2r = 0.48
     target = im * 0.9
     phat, gv, gm, out2 = R.project_residual_step(gd, v, f32, lab, mus, idx, target)
     assert torch.equal(phat, im)

@@ -38,14 +38,17 @@ def test_vertex_forward_vs_reference_modules(cuda_lib, path):
     assert gd.max_sino_val == g["msv"]
     p6, len3, ff = R.vertex_forward(gd, dev(g["verts"], torch.float32), dev(g["faces"], torch.int32), g["idx_angles"])
     torch.cuda.synchronize()
-    tol_px = 1e-3 if geom["type"] == "cone_vec" else 1e-4        # float32 op-order noise
+    # float32 op-order noise.  Measured on a B200 (round 2): 1.7e-4 px (cone_vec), 1.5e-5 px
+    # (parallel3d), 0 (parallel3d_vec: bit-identical) vs the reference's fp32 modules on the torch CPU device —
+    # the same distance the reference's own fp32 run has from its fp64 run (1.8e-4 / 1.6e-5 / 6e-5 px).  Bound = 2x.
+    tol_px = {"cone_vec": 4e-4, "parallel3d": 4e-5, "parallel3d_vec": 1e-6}[geom["type"]]
     g64 = np.load(path.replace("_f32", "_f64"))                   # the reference modules in float64: the true values
     e_px, e_len = np.abs(p6.cpu().numpy() - g["p6"]).max(), np.abs(len3.cpu().numpy() - g["len3"]).max()
     print(f"[{geom['type']}] vertex stage vs reference fp32 modules: max |dp| = {e_px:.2e} px, max |dlen| = {e_len:.2e}; "
           f"vs reference fp64: {np.abs(p6.cpu().numpy() - g64['p6']).max():.2e} px (reference fp32 vs its own fp64: "
           f"{np.abs(g['p6'] - g64['p6']).max():.2e} px)")
     assert e_px <= tol_px
-    assert e_len <= 5e-6
+    assert e_len <= 2e-6                                          # measured: <= 9.5e-7 (one ulp of len ~ 10)
     big = np.abs(g["ff"]) > 1e-6
     assert np.array_equal((ff.cpu().numpy() < 0)[big], (g["ff"] < 0)[big])
 
@@ -99,11 +102,12 @@ def test_fused_forward_equals_staged_and_oracle(cuda_lib, kind):
     q6, l3, f1, msv = vertex_stage.vertex_stage(geom, mesh[0], mesh[1], np.arange(6), np.float32)
     o2 = oracle.rasterizer_forward(q6, l3, f1, mesh[2], mesh[3], gd.H, gd.W, msv, False, fast=True)
     diff = cnt.cpu().numpy() != o2["cnt"][..., 0]
-    assert diff.mean() < 2e-4, f"{diff.sum()} coverage mismatches"
+    assert diff.mean() < 5e-5, f"{diff.sum()} coverage mismatches"       # measured (round 2): 0 of 153600 for all three kinds
     same = ~diff
     a, b = im.cpu().numpy()[same], o2["im"][..., 0][same]
     depth = max(int(o2["cnt"].max()), 1)
-    tol = 1e-5 * np.abs(b) + 4 * depth * np.spacing(np.float32(l3.max())) * np.abs(mesh[3]).max() + 1e-4 * (kind == "cone_vec")
+    # the stated forward tolerance with no extra allowance for cone (measured: identical bits)
+    tol = 1e-5 * np.abs(b) + 4 * depth * np.spacing(np.float32(l3.max())) * np.abs(mesh[3]).max()
     print(f"[{kind}] fused sinogram vs NumPy-vertex-stage oracle: {int(diff.sum())} knife-edge pixels of {diff.size}, "
           f"max |d im| = {np.abs(a - b).max():.2e}, max (|d im| - 1e-5|im|) = {(np.abs(a - b) - 1e-5 * np.abs(b)).max():.2e}, "
           f"base tol term = {4 * depth * np.spacing(np.float32(l3.max())) * np.abs(mesh[3]).max():.2e}")
@@ -322,9 +326,14 @@ def test_linked_sweeps_equal_unlinked(cuda_lib, monkeypatch, name):
     B = geom["Vectors"].shape[0] if "Vectors" in geom else len(geom["ProjectionAngles"])
     idx = torch.arange(B, device="cuda")
     target = torch.rand(B, gd.H, gd.W, device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    from shapefromprojections_b200 import _lib
     monkeypatch.setenv("CTDR_NO_BATCH_RECORDS", "1")
-    ph0, gv0, gm0, o0 = R.project_residual_step(gd, v, f32, labels, mus, idx, target)
-    monkeypatch.delenv("CTDR_NO_BATCH_RECORDS")
+    _lib.reload_tuning()                                   # the library reads its CTDR_* variables once, not per launch
+    try:
+        ph0, gv0, gm0, o0 = R.project_residual_step(gd, v, f32, labels, mus, idx, target)
+    finally:
+        monkeypatch.delenv("CTDR_NO_BATCH_RECORDS")
+        _lib.reload_tuning()
     ph1, gv1, gm1, o1 = R.project_residual_step(gd, v, f32, labels, mus, idx, target)
     assert torch.equal(ph0, ph1)
     if name == "many_faces_multi_segment":                 # the case does what it is meant to exercise

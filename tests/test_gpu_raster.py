@@ -233,24 +233,28 @@ def test_empty_inputs(cuda_lib):
 def test_fine_mesh_variant_direct_walk(cuda_lib, monkeypatch, name, max_box):
     """The face-per-lane walk of the fine-mesh kernel variant (normally chosen when F >= 0.4*H*W) forced on
     ordinary cases: max_box 4 mixes direct and general batches inside one launch, 4096 walks everything
-    directly.  Forward stays bit-identical to the oracle; the backward equals the default kernels' result up
-    to the order in which a face's fragments are summed."""
+    directly.  Forward stays bit-identical to the oracle (the backward walks row spans and is not affected)."""
     from shapefromprojections_b200.function import rasterizer as R
     c = CASES[name]()
     B, H, W = c["p6"].shape[0], c["H"], c["W"]
     ref = oracle.rasterizer_forward(c["p6"], c["len3"], c["ff"], c["labels"], c["mus"], H, W, c["msv"], False, fast=True)
     g = dev(np.random.default_rng(3).normal(size=(B, H, W, 1)).astype(np.float32))
     args = (dev(c["p6"]), dev(c["len3"]), dev(c["ff"]), dev(c["labels"]), dev(c["mus"]))
-    monkeypatch.setenv("CTDR_DIRECT_MAX_BOX", "0")
+    from shapefromprojections_b200 import _lib
     base = R.raster_backward(g, dev(ref["im"]), *args, c["msv"])
     monkeypatch.setenv("CTDR_DIRECT_MAX_BOX", str(max_box))
-    for want_stats in (True, False):                        # both the counting and the lean instantiation
-        im, cnt, stats = R.raster_forward(*args, H, W, c["msv"], want_cnt=True, want_stats=want_stats)
-        assert np.array_equal(cnt.cpu().numpy(), ref["cnt"])
-        assert np.array_equal(bits(im.cpu().numpy()), bits(ref["im"]))
-        if want_stats:
-            assert stats[1].item() == ref["cnt"].sum() and stats[0].item() == ref["n_nonpositive_len"]
-    got = R.raster_backward(g, dev(ref["im"]), *args, c["msv"])
+    _lib.reload_tuning()                                    # the library reads its CTDR_* variables once, not per launch
+    try:
+        for want_stats in (True, False):                    # both the counting and the lean instantiation
+            im, cnt, stats = R.raster_forward(*args, H, W, c["msv"], want_cnt=True, want_stats=want_stats)
+            assert np.array_equal(cnt.cpu().numpy(), ref["cnt"])
+            assert np.array_equal(bits(im.cpu().numpy()), bits(ref["im"]))
+            if want_stats:
+                assert stats[1].item() == ref["cnt"].sum() and stats[0].item() == ref["n_nonpositive_len"]
+        got = R.raster_backward(g, dev(ref["im"]), *args, c["msv"])     # the backward has no such variant: unchanged
+    finally:
+        monkeypatch.delenv("CTDR_DIRECT_MAX_BOX")
+        _lib.reload_tuning()
     for a, b in zip(got, base):
         assert (a - b).norm().item() <= 2e-5 * b.norm().item() + 1e-30
 
