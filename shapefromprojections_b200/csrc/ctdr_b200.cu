@@ -455,6 +455,7 @@ int check_geom(int kind) {
 
 struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
+    float4* gvt;         // [window, V] per-vertex cotangents of the raster backward (default backward)
     float4* vt;          // [window, V] per-vertex transform records
     float* fs;           // [window, F] per-face attenuation terms (deterministic backward)
     double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
@@ -481,12 +482,12 @@ size_t batch_record_bytes_per_angle(int F, int H, int W) {
 
 size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+    return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) * (bwd ? 2 : 1) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
            MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
-    const size_t slack = 26 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    const size_t slack = 28 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
     const size_t per = project_per_angle_bytes(V, F, bwd, H, W);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -501,8 +502,9 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
     ws->len3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
     ws->ff = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 4, 256);
-    ws->gp6 = ws->glen3 = nullptr;
+    ws->gp6 = ws->glen3 = nullptr; ws->gvt = nullptr;
     if (bwd) {
+        ws->gvt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
         ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
         ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
         ws->fs = reinterpret_cast<float*>(p + off);    off += align_up((size_t)win * F * 4, 256);
@@ -554,6 +556,19 @@ int launch_vertex_backward(const VertexParams& P, const float* gp6, const float*
     dim3 grid((unsigned)face_blocks, (unsigned)((P.B + per - 1) / per));
     k_vertex_backward<<<grid, 256, 0, st>>>(P, gp6, glen3, grad_verts, per);
     CTDR_LAUNCHED(1, "k_vertex_backward launch");
+    return 0;
+}
+
+int launch_vertex_backward_pervertex(const VertexParams& P, const float4* gvt, float* grad_verts, cudaStream_t st) {
+    // enough angle slices to fill the machine, few enough to keep atomics per vertex low
+    int slices = 1;
+    const long long vblocks = (P.V + 255) / 256;
+    while (slices < P.B && vblocks * slices < 16 * 148 && slices < 128) slices <<= 1;
+    if (slices > P.B) slices = P.B;
+    const int per = (P.B + slices - 1) / slices;
+    dim3 grid((unsigned)vblocks, (unsigned)((P.B + per - 1) / per));
+    k_vertex_backward_pervertex<<<grid, 256, 0, st>>>(P, gvt, grad_verts, per);
+    CTDR_LAUNCHED(1, "k_vertex_backward_pervertex launch");
     return 0;
 }
 
@@ -719,7 +734,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 26 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    return per * (size_t)win + 28 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -798,11 +813,16 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
-        CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
-        CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
+        if (det) {      // single-writer kernels keep the per-corner layout
+            CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
+            CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        } else {        // default: cotangents summed per (angle, vertex) by the raster backward itself
+            CTDR_CUDA(cudaMemsetAsync(ws.gvt, 0, (size_t)nb * V * sizeof(float4), stream), "memset grad_vt");
+            P.grad_vt = ws.gvt; P.faces = faces; P.V = V;
+        }
         if (det) {
             if (target) { P.target = target + (size_t)b0 * hw; P.out2 = out2; P.mask_hi = (float)(max_sino_val - 1e-6); }
             else P.grad_im = grad_im + (size_t)b0 * hw;
@@ -820,7 +840,7 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
             P.grad_im = grad_im + (size_t)b0 * hw;
             if (int rc = launch_raster<MODE_BWD>(P, flags, stream)) return rc;
         }
-        if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
+        if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc;
     }
     return 0;
 }
@@ -884,8 +904,12 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream, linked)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_RASTER_FORWARD, stream);
         if (linked) P.bmode = 2;
-        CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
-        CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        if (det) {      // single-writer kernels keep the per-corner layout
+            CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
+            CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
+        } else {        // default: cotangents summed per (angle, vertex) by the raster backward itself
+            CTDR_CUDA(cudaMemsetAsync(ws.gvt, 0, (size_t)nb * V * sizeof(float4), stream), "memset grad_vt");
+        }
         CTDR_MARK(tm, CTDR_STAGE_MEMSET, stream);
         P.im = nullptr;
         P.im_in = phat + (size_t)b0 * hw;
@@ -893,6 +917,7 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         P.out2 = out2;
         P.mask_hi = (float)(max_sino_val - 1e-6);
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
+        if (!det) { P.grad_vt = ws.gvt; P.faces = faces; P.V = V; }
         P.stats = nullptr;                                   // counters describe the forward sweep only
         if (det) {
             if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, true, flags, stream)) return rc;
@@ -903,7 +928,7 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         if (linked) { if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc; }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_RASTER_STEP, stream);
-        if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
+        if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_VERTEX_BACKWARD, stream);
     }
     return 0;

@@ -69,6 +69,12 @@ struct RasterParams {
     float* grad_p6;         // [B,F,6]
     float* grad_len3;       // [B,F,3]
     float* grad_mus;        // [n_mus]
+    // fused projector: cotangents go straight to the projected VERTICES instead of the face corners — per angle a
+    // [V] array of float4 {d/dpx, d/dpy, d/dlen, -} (six times smaller than grad_p6 + grad_len3 to zero, to RED
+    // into and to read back; the scatter over `faces` that autograd's index_backward does, fp_vecs.py:176-186)
+    float4* grad_vt;        // [B,V] or null (then grad_p6 / grad_len3 are written)
+    const int* faces;       // [F,3] vertex ids, needed with grad_vt
+    int V;
     // MODE_STEP
     const float* target;    // [B,H,W]
     float mask_hi;          // float32(max_sino_val - 1e-6), get_valid_mask upper bound (fp_vecs.py:13)
@@ -580,6 +586,10 @@ __device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -1116,6 +1126,8 @@ struct __align__(16) ReplayWarpSmem {
     float  acc[TILE_PIX];                   // g (0 where no gradient)
     int    landing[2][36];                  // the next two batch records in flight (cp.async): {next, count, 32 face ids}
     int    qface[32];                       // faces of the current batch
+    float  fdata[32 * 8];                   // per lane: the projected face (ax,ay,bx,by,cx,cy) + its pixel box, staged by
+                                            // cp.async one batch ahead (the kernel is latency-bound on exactly these loads)
 };
 __device__ __forceinline__ double* prefix_e0(ReplayWarpSmem& S) { return S.pre; }
 
@@ -1225,10 +1237,15 @@ __device__ __noinline__ float4 bwd_row_exact(const float* __restrict__ p6row, co
     return make_float4(M0, A1, A2, __int_as_float(cnt));
 }
 
-template <class ThreadStats, class WS>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// fsrc: per-lane staged face data in shared memory (8 floats: ax,ay,bx,by,cx,cy, box) or null (global loads);
+// after_load(): called once the batch's face data sits in registers (the replay kernel then overwrites the
+// staging area with the next batch's)
+template <class ThreadStats, class WS, class Hook = NoHook>
 __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S, float* gmus,
                                                    int b, int nb, int tx0, int ty0, int tx1, int ty1,
-                                                   int lane, ThreadStats& st) {
+                                                   int lane, ThreadStats& st, const float* fsrc = nullptr, Hook after_load = Hook()) {
     const bool queued = lane < nb;
     const int f = queued ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
@@ -1242,16 +1259,25 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         int cx0 = 0, cy0 = 0, bw = 1, bh = 0;
         float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
         if (queued) {
-            const short4 fb = __ldg(P.face_box + bf);
-            const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-            ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+            short4 fb;
+            if (fsrc) {
+                const float4 u = reinterpret_cast<const float4*>(fsrc)[2 * lane], w = reinterpret_cast<const float4*>(fsrc)[2 * lane + 1];
+                ax = u.x; ay = u.y; bx = u.z; by = u.w; cx = w.x; cy = w.y;
+                const int b0 = __float_as_int(w.z), b1 = __float_as_int(w.w);
+                fb = make_short4((short)(b0 & 0xffff), (short)(b0 >> 16), (short)(b1 & 0xffff), (short)(b1 >> 16));
+            } else {
+                fb = __ldg(P.face_box + bf);
+                const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+                ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+            }
             cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
             bw = min((int)fb.z, tx1) - cx0 + 1;
             bh = min((int)fb.w, ty1) - cy0 + 1;
             prefetch_l1(P.len3 + bf * 3);               // the epilogue's operands travel while the rows are walked
             prefetch_l1(P.ff + bf);
         }
-        __syncwarp();                                   // queue entries consumed
+        __syncwarp();                                   // queue entries and staged face data consumed
+        after_load();
         if (lane == 0) st.visits++;
         const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
         const int x_hi = cx0 + bw - 1;
@@ -1330,13 +1356,22 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         const float cgeo = sgn * (mu_in - mu_out);                    // raw mu, no label-0 flip (back.cu:115)
         float gp[6], gl[3], bsum;
         face_grads_from_moments(es, r0, r1, r2, cgeo, M0, A1, A2, gp, gl, bsum);
-        float* dl = P.grad_len3 + bf * 3;                             // back.cu:126-136
-        atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
         // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
         st.mus_add(gmus, lab.x, (lab.x == 0 ? -sgn : sgn) * bsum, lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
-        float* dp = P.grad_p6 + bf * 6;                               // back.cu:285-292
+        if (P.grad_vt) {
+            // one vector RED per corner onto the corner's vertex (back.cu:126-136 and :285-292 merged)
+            const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
+            float4* gv = P.grad_vt + (long long)b * P.V;
+            atomicAdd(gv + i0, make_float4(gp[0], gp[1], gl[0], 0.0f));
+            atomicAdd(gv + i1, make_float4(gp[2], gp[3], gl[1], 0.0f));
+            atomicAdd(gv + i2, make_float4(gp[4], gp[5], gl[2], 0.0f));
+        } else {
+            float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
+            atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
+            float* dp = P.grad_p6 + bf * 6;                           // back.cu:285-292
 #pragma unroll
-        for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
+            for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
+        }
     }
     __syncwarp();
 }
@@ -1468,8 +1503,20 @@ k_step_replay(const RasterParams P) {
                 vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
                 tt[k] = ok ? __ldg(P.target + o) : 0.0f;
             }
-            // Record pipeline: while batch k is processed, record k+1 has landed (its faces' data is being pulled
-            // into L2 by prefetches) and record k+2 is in flight.  `cur` holds batch k's faces.
+            // Pipeline, two records deep: while batch k is processed, the face data of batch k+1 (projected vertices +
+            // pixel box, 32 B per face) is being copied into shared memory by cp.async — its record landed one batch
+            // earlier — and record k+2 is in flight.  At the top of an iteration everything outstanding was issued a
+            // whole batch ago.
+            auto stage_faces = [&](int fid, int n) {
+                if (lane < n) {
+                    const long long bf = (long long)b * P.F + fid;
+                    float* dst = S.fdata + lane * 8;
+                    const float* src = P.p6 + bf * 6;
+                    cp_async8(dst, src); cp_async8(dst + 2, src + 2); cp_async8(dst + 4, src + 4);
+                    cp_async8(dst + 6, P.face_box + bf);
+                    prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
+                }
+            };
             int nbatch = 0, next = -1, id = 0, slot = 0;
             if (roff0 >= 0) {
                 cp_async_wait_all();
@@ -1478,11 +1525,7 @@ k_step_replay(const RasterParams P) {
                 next = L0[0]; nbatch = L0[1]; id = L0[2 + lane];
                 if (next >= 0) prefetch_record(P, S.landing[1], next, lane);
                 slot = 1;
-                if (lane < nbatch) {                          // the first batch's face data: on its way during the g / prefix work
-                    const long long bf = (long long)b * P.F + id;
-                    prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
-                    prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
-                }
+                stage_faces(id, nbatch);                      // the first batch's faces: on their way during the g / prefix work
             }
 #pragma unroll
             for (int k = 0; k < TILE / 2; ++k) {
@@ -1501,22 +1544,17 @@ k_step_replay(const RasterParams P) {
                 if (lane < nbatch) S.qface[lane] = id;
                 const int nb_cur = nbatch;
                 const bool more = next >= 0;
+                cp_async_wait_all();                                  // this batch's face data (+ the next record)
+                __syncwarp();
                 if (more) {
-                    // record k+1 has landed: read it, prefetch its faces' data towards L2, start record k+2
-                    cp_async_wait_all();
-                    __syncwarp();
                     const int* L = S.landing[slot];
                     next = L[0]; nbatch = L[1]; id = L[2 + lane];
                     slot ^= 1;
                     if (next >= 0) prefetch_record(P, S.landing[slot], next, lane);
-                    if (lane < nbatch) {
-                        const long long bf = (long long)b * P.F + id;
-                        prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
-                        prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
-                    }
                 }
                 __syncwarp();
-                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
+                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st, S.fdata,
+                                   [&]() { if (more) stage_faces(id, nbatch); });
                 if (!more) break;
             }
         }

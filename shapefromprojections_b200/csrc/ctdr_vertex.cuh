@@ -318,4 +318,31 @@ k_vertex_backward(const VertexParams P, const float* __restrict__ grad_p6,
     }
 }
 
+// Fused projector: the raster backward has already summed the corner cotangents per (angle, vertex)
+// (RasterParams::grad_vt), so the transposed vertex stage is thread per vertex, angle slices along grid.y: no face
+// gather, coalesced float4 reads, three atomics per (vertex, slice).
+__global__ void __launch_bounds__(256)
+k_vertex_backward_pervertex(const VertexParams P, const float4* __restrict__ grad_vt, float* __restrict__ grad_verts,
+                            int angles_per_slice) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= P.V) return;
+    const int b0 = blockIdx.y * angles_per_slice, b1 = min(b0 + angles_per_slice, P.B);
+    const float x = __ldg(P.verts + 3 * v), y = __ldg(P.verts + 3 * v + 1), z = __ldg(P.verts + 3 * v + 2);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    bool any = false;
+    for (int b = b0; b < b1; ++b) {
+        const float4 g = __ldg(grad_vt + (long long)b * P.V + v);
+        if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f) continue;
+        any = true;
+        const AngleConst A = angle_const(P, b);
+        float gx, gy, gz;
+        vertex_vjp(P, A, x, y, z, g.x, g.y, g.z, gx, gy, gz);
+        ax += gx; ay += gy; az += gz;
+    }
+    if (!any) return;
+    atomicAdd(grad_verts + 3 * v + 0, ax);
+    atomicAdd(grad_verts + 3 * v + 1, ay);
+    atomicAdd(grad_verts + 3 * v + 2, az);
+}
+
 }  // namespace ctdr
