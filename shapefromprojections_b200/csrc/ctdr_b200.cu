@@ -81,12 +81,14 @@ struct Tuning {
     int region_major = 1;        // CTDR_REGION_MAJOR: CTA order of k_raster (measured: 1 wins)
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
+    int grad_per_vertex = 1;     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
     void load() {
         *this = Tuning();
         if (const char* e = getenv("CTDR_REGION_TILES")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) region_tiles = v; }
         if (const char* e = getenv("CTDR_REGION_MAJOR")) region_major = atoi(e) != 0;
         if (const char* e = getenv("CTDR_DIRECT_MAX_BOX")) direct_max_box = atoi(e) < 0 ? -1 : atoi(e);
         no_batch_records = getenv("CTDR_NO_BATCH_RECORDS") != nullptr;
+        if (const char* e = getenv("CTDR_GRAD_PER_VERTEX")) grad_per_vertex = atoi(e);
     }
 };
 Tuning& tuning() {
@@ -816,10 +818,11 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
-        if (det) {      // single-writer kernels keep the per-corner layout
+        const bool pervertex = !det && tuning().grad_per_vertex != 0;
+        if (!pervertex) {   // single-writer kernels (and the tuning fallback) keep the per-corner layout
             CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
             CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
-        } else {        // default: cotangents summed per (angle, vertex) by the raster backward itself
+        } else {            // default: cotangents summed per (angle, vertex) by the raster backward itself
             CTDR_CUDA(cudaMemsetAsync(ws.gvt, 0, (size_t)nb * V * sizeof(float4), stream), "memset grad_vt");
             P.grad_vt = ws.gvt; P.faces = faces; P.V = V;
         }
@@ -840,7 +843,8 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
             P.grad_im = grad_im + (size_t)b0 * hw;
             if (int rc = launch_raster<MODE_BWD>(P, flags, stream)) return rc;
         }
-        if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc;
+        if (pervertex) { if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc; }
+        else if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
     }
     return 0;
 }
@@ -904,7 +908,8 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         if (int rc = launch_raster<MODE_FWD>(P, flags, stream, linked)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_RASTER_FORWARD, stream);
         if (linked) P.bmode = 2;
-        if (det) {      // single-writer kernels keep the per-corner layout
+        const bool pervertex = !det && tuning().grad_per_vertex != 0;
+        if (!pervertex) {   // single-writer kernels (and the tuning fallback) keep the per-corner layout
             CTDR_CUDA(cudaMemsetAsync(ws.gp6, 0, (size_t)nb * F * 24, stream), "memset grad_p6");
             CTDR_CUDA(cudaMemsetAsync(ws.glen3, 0, (size_t)nb * F * 12, stream), "memset grad_len3");
         } else {        // default: cotangents summed per (angle, vertex) by the raster backward itself
@@ -917,7 +922,7 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         P.out2 = out2;
         P.mask_hi = (float)(max_sino_val - 1e-6);
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
-        if (!det) { P.grad_vt = ws.gvt; P.faces = faces; P.V = V; }
+        if (pervertex) { P.grad_vt = ws.gvt; P.faces = faces; P.V = V; }
         P.stats = nullptr;                                   // counters describe the forward sweep only
         if (det) {
             if (int rc = deterministic_window(P, VP, ws, vadj_start, vadj_corner, grad_verts, true, flags, stream)) return rc;
@@ -928,7 +933,8 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         if (linked) { if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc; }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_RASTER_STEP, stream);
-        if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc;
+        if (pervertex) { if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc; }
+        else if (int rc = launch_vertex_backward(VP, ws.gp6, ws.glen3, grad_verts, stream)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_VERTEX_BACKWARD, stream);
     }
     return 0;

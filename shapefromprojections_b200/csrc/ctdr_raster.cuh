@@ -587,10 +587,6 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -1126,8 +1122,6 @@ struct __align__(16) ReplayWarpSmem {
     float  acc[TILE_PIX];                   // g (0 where no gradient)
     int    landing[2][36];                  // the next two batch records in flight (cp.async): {next, count, 32 face ids}
     int    qface[32];                       // faces of the current batch
-    float  fdata[32 * 8];                   // per lane: the projected face (ax,ay,bx,by,cx,cy) + its pixel box, staged by
-                                            // cp.async one batch ahead (the kernel is latency-bound on exactly these loads)
 };
 __device__ __forceinline__ double* prefix_e0(ReplayWarpSmem& S) { return S.pre; }
 
@@ -1237,15 +1231,10 @@ __device__ __noinline__ float4 bwd_row_exact(const float* __restrict__ p6row, co
     return make_float4(M0, A1, A2, __int_as_float(cnt));
 }
 
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
-
-// fsrc: per-lane staged face data in shared memory (8 floats: ax,ay,bx,by,cx,cy, box) or null (global loads);
-// after_load(): called once the batch's face data sits in registers (the replay kernel then overwrites the
-// staging area with the next batch's)
-template <class ThreadStats, class WS, class Hook = NoHook>
+template <class ThreadStats, class WS>
 __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S, float* gmus,
                                                    int b, int nb, int tx0, int ty0, int tx1, int ty1,
-                                                   int lane, ThreadStats& st, const float* fsrc = nullptr, Hook after_load = Hook()) {
+                                                   int lane, ThreadStats& st) {
     const bool queued = lane < nb;
     const int f = queued ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
@@ -1259,25 +1248,16 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         int cx0 = 0, cy0 = 0, bw = 1, bh = 0;
         float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
         if (queued) {
-            short4 fb;
-            if (fsrc) {
-                const float4 u = reinterpret_cast<const float4*>(fsrc)[2 * lane], w = reinterpret_cast<const float4*>(fsrc)[2 * lane + 1];
-                ax = u.x; ay = u.y; bx = u.z; by = u.w; cx = w.x; cy = w.y;
-                const int b0 = __float_as_int(w.z), b1 = __float_as_int(w.w);
-                fb = make_short4((short)(b0 & 0xffff), (short)(b0 >> 16), (short)(b1 & 0xffff), (short)(b1 >> 16));
-            } else {
-                fb = __ldg(P.face_box + bf);
-                const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-                ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
-            }
+            const short4 fb = __ldg(P.face_box + bf);
+            const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+            ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
             cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
             bw = min((int)fb.z, tx1) - cx0 + 1;
             bh = min((int)fb.w, ty1) - cy0 + 1;
             prefetch_l1(P.len3 + bf * 3);               // the epilogue's operands travel while the rows are walked
             prefetch_l1(P.ff + bf);
         }
-        __syncwarp();                                   // queue entries and staged face data consumed
-        after_load();
+        __syncwarp();                                   // queue entries consumed
         if (lane == 0) st.visits++;
         const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
         const int x_hi = cx0 + bw - 1;
@@ -1432,6 +1412,7 @@ __device__ __forceinline__ void prefetch_record(const RasterParams& P, int* L, i
     if (lane < 2) cp_async4(L + lane, r + lane);
 }
 
+// 8 resident CTAs (64 registers); 9 CTAs at 56 registers was measured slower (5.06 -> 6.19 ms on config 3)
 template <bool STATS>
 __global__ void __launch_bounds__(THREADS, 8)
 k_step_replay(const RasterParams P) {
@@ -1503,17 +1484,14 @@ k_step_replay(const RasterParams P) {
                 vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
                 tt[k] = ok ? __ldg(P.target + o) : 0.0f;
             }
-            // Pipeline, two records deep: while batch k is processed, the face data of batch k+1 (projected vertices +
-            // pixel box, 32 B per face) is being copied into shared memory by cp.async — its record landed one batch
-            // earlier — and record k+2 is in flight.  At the top of an iteration everything outstanding was issued a
-            // whole batch ago.
+            // Pipeline, two records deep: while batch k is processed, record k+1 has landed — the data of its faces
+            // (pixel box, projected vertices, lengths, facing) is being pulled into L2 by prefetches — and record k+2 is
+            // in flight.  The kernel is latency-bound on exactly these loads (ncu: 53 % of its stall samples were
+            // long-scoreboard before); staging the face data in shared memory by cp.async instead was measured slower.
             auto stage_faces = [&](int fid, int n) {
                 if (lane < n) {
                     const long long bf = (long long)b * P.F + fid;
-                    float* dst = S.fdata + lane * 8;
-                    const float* src = P.p6 + bf * 6;
-                    cp_async8(dst, src); cp_async8(dst + 2, src + 2); cp_async8(dst + 4, src + 4);
-                    cp_async8(dst + 6, P.face_box + bf);
+                    prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
                     prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
                 }
             };
@@ -1544,17 +1522,17 @@ k_step_replay(const RasterParams P) {
                 if (lane < nbatch) S.qface[lane] = id;
                 const int nb_cur = nbatch;
                 const bool more = next >= 0;
-                cp_async_wait_all();                                  // this batch's face data (+ the next record)
-                __syncwarp();
                 if (more) {
+                    cp_async_wait_all();                              // record k+1, issued a whole batch ago
+                    __syncwarp();
                     const int* L = S.landing[slot];
                     next = L[0]; nbatch = L[1]; id = L[2 + lane];
                     slot ^= 1;
                     if (next >= 0) prefetch_record(P, S.landing[slot], next, lane);
+                    stage_faces(id, nbatch);
                 }
                 __syncwarp();
-                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st, S.fdata,
-                                   [&]() { if (more) stage_faces(id, nbatch); });
+                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
                 if (!more) break;
             }
         }
