@@ -81,7 +81,8 @@ struct Tuning {
     int region_major = 1;        // CTDR_REGION_MAJOR: CTA order of k_raster (measured: 1 wins)
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
-    int grad_per_vertex = 1;     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
+    int grad_per_vertex = 1;
+    int gather = 1;              // CTDR_GATHER: 1 = fused raster kernels gather corners from the per-vertex records (no p6/len3/ff), 0 = face arrays     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
     void load() {
         *this = Tuning();
         if (const char* e = getenv("CTDR_REGION_TILES")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) region_tiles = v; }
@@ -89,6 +90,7 @@ struct Tuning {
         if (const char* e = getenv("CTDR_DIRECT_MAX_BOX")) direct_max_box = atoi(e) < 0 ? -1 : atoi(e);
         no_batch_records = getenv("CTDR_NO_BATCH_RECORDS") != nullptr;
         if (const char* e = getenv("CTDR_GRAD_PER_VERTEX")) grad_per_vertex = atoi(e);
+        if (const char* e = getenv("CTDR_GATHER")) gather = atoi(e) != 0;
     }
 };
 Tuning& tuning() {
@@ -141,7 +143,7 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
         const long long warps = (long long)P.B * P.NC;
         const long long blocks = (warps + WARPS - 1) / WARPS;
         if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
-        k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
+        k_chunk_bbox<<<(unsigned)blocks, THREADS, 0, st>>>(P.p6, P.ff, P.labels2, P.B, P.F, P.H, P.W, P.NC, boxes, face_boxes);
         CTDR_LAUNCHED(1, "k_chunk_bbox launch");
     }
     if (P.slist) {      // tile-binned modes: coarse (super-region) lists for phase A of k_raster
@@ -155,10 +157,20 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
     return 0;
 }
 
-template <int MODE, bool DIRECT, bool LINKED>
+template <int MODE, bool DIRECT, bool LINKED, bool GATHER>
 void launch_raster_variant(const RasterParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
-    if (P.stats) k_raster<MODE, false, DIRECT, true, LINKED><<<blocks, THREADS, smem, st>>>(P);
-    else k_raster<MODE, false, DIRECT, false, LINKED><<<blocks, THREADS, smem, st>>>(P);
+    if (P.stats) k_raster<MODE, false, DIRECT, true, LINKED, GATHER><<<blocks, THREADS, smem, st>>>(P);
+    else k_raster<MODE, false, DIRECT, false, LINKED, GATHER><<<blocks, THREADS, smem, st>>>(P);
+}
+
+// gather (P.vt != null, fused projector only): the kernels instantiated for corner gathers from the vertex records
+template <int MODE, bool DIRECT, bool LINKED>
+void launch_raster_gather(const RasterParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    constexpr bool CAN_GATHER = (MODE == MODE_FWD || MODE == MODE_BWD || MODE == MODE_STEP);
+    if constexpr (CAN_GATHER) {
+        if (P.vt) { launch_raster_variant<MODE, DIRECT, LINKED, true>(P, blocks, smem, st); return; }
+    }
+    launch_raster_variant<MODE, DIRECT, LINKED, false>(P, blocks, smem, st);
 }
 
 // linked: MODE_FWD records its face batches, MODE_STEP is the replay-only kernel (see k_raster)
@@ -177,23 +189,30 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool l
     // fine meshes (about a pixel per face): the forward walks batches of small boxes face-per-lane (DIRECT); the
     // backward modes walk row spans face-per-lane in any case (process_batch_rows)
     const bool direct = MODE == MODE_FWD && P.direct_max_box > 0;
+    if (P.vt && (MODE == MODE_FRAG || MODE == MODE_MULTI || (flags & CTDR_FLAG_NO_PREFILTER)))
+        return fail(CTDR_E_SHAPE, "internal: this raster mode reads the face arrays, not vertex records");
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate (never linked)
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else if (linked && MODE == MODE_STEP) {
         // replay-only residual/backward kernel over the batches the forward sweep recorded
-        if (P.stats) k_step_replay<true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
-        else k_step_replay<false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        if (P.vt) {
+            if (P.stats) k_step_replay<true, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+            else k_step_replay<false, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        } else {
+            if (P.stats) k_step_replay<true, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+            else k_step_replay<false, false><<<(unsigned)blocks, THREADS, smem, st>>>(P);
+        }
     } else if constexpr (MODE == MODE_FWD) {
         if (linked) {
-            if (direct) launch_raster_variant<MODE_FWD, true, true>(P, (unsigned)blocks, smem, st);
-            else launch_raster_variant<MODE_FWD, false, true>(P, (unsigned)blocks, smem, st);
+            if (direct) launch_raster_gather<MODE_FWD, true, true>(P, (unsigned)blocks, smem, st);
+            else launch_raster_gather<MODE_FWD, false, true>(P, (unsigned)blocks, smem, st);
         } else if (direct) {
-            launch_raster_variant<MODE_FWD, true, false>(P, (unsigned)blocks, smem, st);
+            launch_raster_gather<MODE_FWD, true, false>(P, (unsigned)blocks, smem, st);
         } else {
-            launch_raster_variant<MODE_FWD, false, false>(P, (unsigned)blocks, smem, st);
+            launch_raster_gather<MODE_FWD, false, false>(P, (unsigned)blocks, smem, st);
         }
     } else {
-        launch_raster_variant<MODE, false, false>(P, (unsigned)blocks, smem, st);
+        launch_raster_gather<MODE, false, false>(P, (unsigned)blocks, smem, st);
     }
     CTDR_LAUNCHED(1, "k_raster launch");
     return 0;
@@ -413,6 +432,12 @@ RasterParams base_params(const float* p6, const float* ff, const float* len3, co
     return P;
 }
 
+// gather mode of the fused projector: corners come from the per-vertex records, the [B,F] corner arrays do not exist
+void use_vertex_records(RasterParams& P, const float4* vt, const int32_t* faces, int V) {
+    P.vt = vt; P.faces = faces; P.V = V;
+    P.p6 = nullptr; P.len3 = nullptr; P.ff = nullptr;
+}
+
 int raster_backward_impl(RasterParams P, RasterWs ws, unsigned flags, cudaStream_t st) {
     if (flags & CTDR_FLAG_DETERMINISTIC) {
         const long long n = (long long)P.B * P.F;
@@ -482,15 +507,19 @@ size_t batch_record_bytes_per_angle(int F, int H, int W) {
     return batch_records_per_angle(F, H, W) * BREC_INTS * sizeof(int) + 2 * tiles * sizeof(int) + regions2 + sizeof(int);
 }
 
-size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0) {
+// face_arrays: the [B,F] corner arrays (p6/len3/ff, and their gradient twins + per-face terms when bwd) are laid out;
+// the default (gather) mode of the fused projector needs none of them, so its angle windows hold more angles in the
+// same bytes.  The size query always budgets for them (the flags of the later call are not known to it).
+size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0, bool face_arrays = true) {
     const int NC = (F + CHUNK - 1) / CHUNK;
-    return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) * (bwd ? 2 : 1) + (size_t)F * (40 + (bwd ? 36 + 4 : 0) + sizeof(short4)) + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
+    const size_t per_face = (face_arrays ? 40 + (bwd ? 36 + 4 : 0) : 0) + sizeof(short4);
+    return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) * (bwd ? 2 : 1) + (size_t)F * per_face + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
            MAX_SR * MAX_SR * sizeof(int) + 512;
 }
 
-int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws) {
+int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws, bool face_arrays = true) {
     const size_t slack = 28 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
-    const size_t per = project_per_angle_bytes(V, F, bwd, H, W);
+    const size_t per = project_per_angle_bytes(V, F, bwd, H, W, face_arrays);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
     if (win > B) win = B;
@@ -501,15 +530,20 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     char* p = static_cast<char*>(base);
     size_t off = 0;
     ws->vt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
-    ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
-    ws->len3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
-    ws->ff = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 4, 256);
-    ws->gp6 = ws->glen3 = nullptr; ws->gvt = nullptr;
+    ws->p6 = ws->len3 = ws->ff = nullptr;
+    if (face_arrays) {
+        ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
+        ws->len3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
+        ws->ff = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 4, 256);
+    }
+    ws->gp6 = ws->glen3 = ws->fs = nullptr; ws->gvt = nullptr;
     if (bwd) {
         ws->gvt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
-        ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
-        ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
-        ws->fs = reinterpret_cast<float*>(p + off);    off += align_up((size_t)win * F * 4, 256);
+        if (face_arrays) {
+            ws->gp6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
+            ws->glen3 = reinterpret_cast<float*>(p + off); off += align_up((size_t)win * F * 12, 256);
+            ws->fs = reinterpret_cast<float*>(p + off);    off += align_up((size_t)win * F * 4, 256);
+        }
         ws->partials = reinterpret_cast<double*>(p + off); off += align_up(2 * DET_LOSS_BLOCKS * sizeof(double), 256);
         const size_t tiles = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
         const size_t regions2 = (size_t)((W + 2 * TILE - 1) / (2 * TILE)) * ((H + 2 * TILE - 1) / (2 * TILE));
@@ -536,14 +570,17 @@ int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* 
 }
 
 // vertex stage of one angle window in the fused path; also produces the face and chunk pixel boxes
+// full = false: boxes only — the raster kernels gather the corners from `vt` (RasterParams::vt)
 int launch_vertex_forward_staged(const VertexParams& P, float4* vt, const int32_t* labels2, float* p6, float* len3, float* ff,
-                                 short4* face_boxes, short4* chunk_boxes, cudaStream_t st) {
+                                 short4* face_boxes, short4* chunk_boxes, cudaStream_t st, bool full = true) {
     const long long nv = (long long)P.B * P.V;
     if ((nv + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*V too large for one launch");
     if (P.B > 65535) return fail(CTDR_E_SHAPE, "angle window of %d angles > 65535", P.B);
     k_vertex_transform<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(P, vt);
     CTDR_LAUNCHED(1, "k_vertex_transform launch");
-    k_face_assemble<<<dim3((unsigned)((P.F + 255) / 256), (unsigned)P.B), 256, 0, st>>>(P, vt, labels2, p6, len3, ff, face_boxes, chunk_boxes);
+    const dim3 grid((unsigned)((P.F + 255) / 256), (unsigned)P.B);
+    if (full) k_face_assemble<true><<<grid, 256, 0, st>>>(P, vt, labels2, p6, len3, ff, face_boxes, chunk_boxes);
+    else k_face_assemble<false><<<grid, 256, 0, st>>>(P, vt, labels2, nullptr, nullptr, nullptr, face_boxes, chunk_boxes);
     CTDR_LAUNCHED(1, "k_face_assemble launch");
     return 0;
 }
@@ -750,13 +787,15 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
     if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
     if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !im || !workspace) return fail(CTDR_E_NULL, "ctdr_project_forward: null pointer");
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, V, F, H, W, false, workspace, workspace_bytes, &ws)) return rc;
+    const bool gather = tuning().gather != 0 && !(flags & CTDR_FLAG_NO_PREFILTER);   // the debug kernels read the face arrays
+    if (int rc = project_ws_layout(B, V, F, H, W, false, workspace, workspace_bytes, &ws, !gather)) return rc;
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        if (gather) use_vertex_records(P, ws.vt, faces, V);
         P.im = im + (size_t)b0 * hw;
         P.cnt = cnt ? cnt + (size_t)b0 * hw : nullptr;
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
@@ -809,13 +848,17 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
     if (det && (!vadj_start || !vadj_corner))
         return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    // gather mode: corners from the vertex records, cotangents onto the vertices; the single-writer (deterministic) and
+    // debug kernels, and the per-corner gradient fallback, keep the [B,F] face arrays
+    const bool gather = !det && tuning().gather != 0 && tuning().grad_per_vertex != 0 && !(flags & CTDR_FLAG_NO_PREFILTER);
+    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws, !gather)) return rc;
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        if (gather) use_vertex_records(P, ws.vt, faces, V);
         P.im_in = im + (size_t)b0 * hw;
         P.grad_p6 = ws.gp6; P.grad_len3 = ws.glen3; P.grad_mus = grad_mus;
         const bool pervertex = !det && tuning().grad_per_vertex != 0;
@@ -886,14 +929,18 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
     if (det && (!vadj_start || !vadj_corner))
         return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
     ProjectWs ws;
-    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws)) return rc;
+    // gather mode: corners from the vertex records, cotangents onto the vertices; the single-writer (deterministic) and
+    // debug kernels, and the per-corner gradient fallback, keep the [B,F] face arrays
+    const bool gather = !det && tuning().gather != 0 && tuning().grad_per_vertex != 0 && !(flags & CTDR_FLAG_NO_PREFILTER);
+    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws, !gather)) return rc;
     const size_t hw = (size_t)H * W;
     CTDR_MARK(tm, -1, stream);
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
+        if (gather) use_vertex_records(P, ws.vt, faces, V);
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_VERTEX_FORWARD, stream);

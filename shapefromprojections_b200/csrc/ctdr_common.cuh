@@ -52,6 +52,18 @@ __device__ __forceinline__ bool face_int_bbox(float ax, float ay, float bx, floa
     return (ix0 <= ix1) & (iy0 <= iy1);
 }
 
+// The per-face pixel box also carries the face's facing sign (the only thing the rasteriser needs of
+// front_facing_bxfx1, diff_fp_for.cu:94-96) in bit 15 of .x: coordinates are <= 32767, so the bit is free.
+__device__ __forceinline__ short4 pack_box(int x0, int y0, int x1, int y1, bool facing_neg) {
+    return make_short4((short)(x0 | (facing_neg ? 0x8000 : 0)), (short)y0, (short)x1, (short)y1);
+}
+__device__ __forceinline__ short4 unpack_box(short4 fb, bool& facing_neg) {
+    facing_neg = fb.x < 0;
+    fb.x = (short)(fb.x & 0x7fff);
+    return fb;
+}
+__device__ __forceinline__ short4 unpack_box(short4 fb) { fb.x = (short)(fb.x & 0x7fff); return fb; }
+
 // Per-face constants of the barycentric solve (diff_fp_for.cu:126-130,142).
 struct EdgeSetup {
     float ax, ay, m, p, n, q, k3;

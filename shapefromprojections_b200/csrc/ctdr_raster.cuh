@@ -49,7 +49,8 @@ struct RasterParams {
     int RT;                 // tiles per region edge
     int regions_x, regions_y;
     const short4* chunk_box;  // [B,NC] pixel bbox of each chunk (x0,y0,x1,y1), empty: x0 > x1
-    const short4* face_box;   // [B,F]  pixel bbox of each face, empty when the face contributes nowhere
+    const short4* face_box;   // [B,F]  pixel bbox of each face, empty when the face contributes nowhere; bit 15 of .x
+                              // carries the facing sign (front_facing < 0, diff_fp_for.cu:94-96): see unpack_box
     // coarse level: per (angle, super-region) ordered list of the chunks overlapping it
     const int* slist;         // [B, nsr, NC]
     const int* scount;        // [B, nsr]
@@ -73,8 +74,12 @@ struct RasterParams {
     // [V] array of float4 {d/dpx, d/dpy, d/dlen, -} (six times smaller than grad_p6 + grad_len3 to zero, to RED
     // into and to read back; the scatter over `faces` that autograd's index_backward does, fp_vecs.py:176-186)
     float4* grad_vt;        // [B,V] or null (then grad_p6 / grad_len3 are written)
-    const int* faces;       // [F,3] vertex ids, needed with grad_vt
+    const int* faces;       // [F,3] vertex ids, needed with grad_vt / vt
     int V;
+    // fused projector, gather mode: no [B,F] corner arrays at all — a face's projected corners and lengths are
+    // gathered from the per-(angle, vertex) records {px, py, len, -} through `faces` (p6 / len3 / ff are null then;
+    // the gathers fp_vecs.py:176-186 materialises as [B,F,3,*] tensors)
+    const float4* vt;       // [B,V] or null
     // MODE_STEP
     const float* target;    // [B,H,W]
     float mask_hi;          // float32(max_sino_val - 1e-6), get_valid_mask upper bound (fp_vecs.py:13)
@@ -97,11 +102,47 @@ struct RasterParams {
     int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
 };
 
+// Projected corners (and ray lengths) of face f on window angle b: from the Rasterizer-boundary arrays, or —
+// fused projector, P.vt != null — gathered from the per-(angle, vertex) records through the face's vertex ids.
+template <bool GATHER>
+__device__ __forceinline__ void load_face(const RasterParams& P, int b, int f, long long bf,
+                                          float& ax, float& ay, float& bx, float& by, float& cx, float& cy,
+                                          float& r0, float& r1, float& r2) {
+    if (GATHER) {
+        const int* fi = P.faces + 3 * (long long)f;
+        const int i0 = __ldg(fi), i1 = __ldg(fi + 1), i2 = __ldg(fi + 2);
+        const float4* row = P.vt + (long long)b * P.V;
+        const float4 a = __ldg(row + i0), bb = __ldg(row + i1), c = __ldg(row + i2);
+        ax = a.x; ay = a.y; bx = bb.x; by = bb.y; cx = c.x; cy = c.y; r0 = a.z; r1 = bb.z; r2 = c.z;
+    } else {
+        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
+        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+        const float* pl = P.len3 + bf * 3;
+        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+        r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
+    }
+}
+template <bool GATHER>
+__device__ __forceinline__ void load_face_xy(const RasterParams& P, int b, int f, long long bf,
+                                             float& ax, float& ay, float& bx, float& by, float& cx, float& cy) {
+    if (GATHER) {
+        const int* fi = P.faces + 3 * (long long)f;
+        const int i0 = __ldg(fi), i1 = __ldg(fi + 1), i2 = __ldg(fi + 2);
+        const float2* row = reinterpret_cast<const float2*>(P.vt + (long long)b * P.V);
+        const float2 a = __ldg(row + 2 * i0), bb = __ldg(row + 2 * i1), c = __ldg(row + 2 * i2);
+        ax = a.x; ay = a.y; bx = bb.x; by = bb.y; cx = c.x; cy = c.y;
+    } else {
+        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
+        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
+        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-(angle, chunk) pixel bounding boxes; one warp per chunk
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
-k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
+k_chunk_bbox(const float* __restrict__ p6, const float* __restrict__ ff, const int* __restrict__ labels2,
              int B, int F, int H, int W, int NC, short4* __restrict__ chunk_box, short4* __restrict__ face_box) {
     const long long gw = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -120,7 +161,7 @@ k_chunk_bbox(const float* __restrict__ p6, const int* __restrict__ labels2,
             }
         }
     }
-    if (f < F) face_box[(long long)b * F + f] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+    if (f < F) face_box[(long long)b * F + f] = pack_box(x0, y0, x1, y1, __ldg(ff + (long long)b * F + f) < 0.0f);
     x0 = __reduce_min_sync(FULL, x0); y0 = __reduce_min_sync(FULL, y0);
     x1 = __reduce_max_sync(FULL, x1); y1 = __reduce_max_sync(FULL, y1);
     if (lane == 0) chunk_box[gw] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
@@ -315,12 +356,12 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1;
+    bool fneg = false;
+    float l0 = 0, l1 = 0, l2 = 0;
     if (mine) {
-        const short4 fb = __ldg(P.face_box + bf);
+        const short4 fb = unpack_box(__ldg(P.face_box + bf), fneg);
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
-        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
-        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+        load_face<false>(P, b, f, bf, ax, ay, bx, by, cx, cy, l0, l1, l2);
         cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
         bw = min((int)fb.z, tx1) - cx0 + 1;
         ncand = bw * (min((int)fb.w, ty1) - cy0 + 1);
@@ -351,9 +392,8 @@ __device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S
         reinterpret_cast<double2*>(sl)[2] = make_double2(d, 1.0 / d);
         float cA = 0.0f, cB = 0.0f;
         if (!IS_FRAG) {
-            const float* pl = P.len3 + bf * 3;
-            r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
-            if (__ldg(P.ff + bf) < 0.0f) sgn = -1.0f;                 // diff_fp_for.cu:94-96
+            r0 = l0; r1 = l1; r2 = l2;
+            if (fneg) sgn = -1.0f;                                    // diff_fp_for.cu:94-96
             if (lab.x == lab.y) sgn = -sgn;                           // :167-169
         }
         if (IS_FWD) {
@@ -713,7 +753,7 @@ __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo,
     return xs <= xe;
 }
 
-template <int MODE, bool EXACT_DIV, bool DIRECT, class ThreadStats>
+template <int MODE, bool EXACT_DIV, bool DIRECT, bool GATHER, class ThreadStats>
 __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
@@ -726,25 +766,21 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     int2 lab = make_int2(0, 0);
     float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
     int cx0 = 0, cy0 = 0, bw = 1, bh = 1;
-    float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0, ffv = 0.0f;
+    float sgn = 1.0f, r0 = 0, r1 = 0, r2 = 0;
+    bool fneg = false;
     if (queued) {
-        const short4 fb = __ldg(P.face_box + bf);
+        const short4 fb = unpack_box(__ldg(P.face_box + bf), fneg);
         lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
-        const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
-        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-        ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+        load_face<GATHER>(P, b, f, bf, ax, ay, bx, by, cx, cy, r0, r1, r2);   // the lengths are in flight while the spans are computed
         cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
         bw = min((int)fb.z, tx1) - cx0 + 1;
         bh = min((int)fb.w, ty1) - cy0 + 1;
-        const float* pl = P.len3 + bf * 3;              // in flight while the spans are computed
-        r0 = __ldg(pl); r1 = __ldg(pl + 1); r2 = __ldg(pl + 2);
-        ffv = __ldg(P.ff + bf);
     }
     __syncwarp();                                       // queue entries consumed
     const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
 
     if (lane == 0) st.visits++;
-    if (ffv < 0.0f) sgn = -1.0f;                                      // diff_fp_for.cu:94-96
+    if (fneg) sgn = -1.0f;                                            // diff_fp_for.cu:94-96
     if (lab.x == lab.y) sgn = -sgn;                                   // :167-169
     // degenerate / NaN faces keep their bounding-box rows (measured: spans pay off even on 2x2 boxes)
     const bool tight = (fabsf(es.k3) > 1e-6f) && (fabsf(es.k3) < 1e10f);
@@ -1205,11 +1241,22 @@ __device__ __forceinline__ SpanSetupB span_setup_bwd(const EdgeSetup& es, float 
 // reference's exact test.  Few scalars in, one float4 out: sum g, sum g*k1, sum g*k2 with k1, k2 evaluated per pixel
 // exactly as the forward does (a zero-area face has k1 = k2 = 0 on every pixel it covers, so its moments — and with
 // them its gradients, before the 1/(k3^2 + eps) factor — are exact zeros like the reference's), and the fragment
-// count.  The face is re-read from its p6 row; nothing of the caller's state has its address taken.
+// count.  The face is re-read (L1 hits); nothing of the caller's state has its address taken.
 // grow = the tile row of g (16 floats); xs/xe/xsi/xei tile-relative columns; y absolute.
-__device__ __noinline__ float4 bwd_row_exact(const float* __restrict__ p6row, const float* grow,
+// src: the face's p6 row, or (vtrow != null, gather mode) its three vertex ids into the angle's vertex records.
+__device__ __noinline__ float4 bwd_row_exact(const void* __restrict__ src, const float4* __restrict__ vtrow, const float* grow,
                                              int xs, int xe, int xsi, int xei, int tx0, int y) {
-    const EdgeSetup es = edge_setup(__ldg(p6row), __ldg(p6row + 1), __ldg(p6row + 2), __ldg(p6row + 3), __ldg(p6row + 4), __ldg(p6row + 5));
+    float ax, ay, bx, by, cx, cy;
+    if (vtrow) {
+        const int* fi = static_cast<const int*>(src);
+        const float2* row = reinterpret_cast<const float2*>(vtrow);
+        const float2 a = __ldg(row + 2 * __ldg(fi)), bb = __ldg(row + 2 * __ldg(fi + 1)), c = __ldg(row + 2 * __ldg(fi + 2));
+        ax = a.x; ay = a.y; bx = bb.x; by = bb.y; cx = c.x; cy = c.y;
+    } else {
+        const float* p6row = static_cast<const float*>(src);
+        ax = __ldg(p6row); ay = __ldg(p6row + 1); bx = __ldg(p6row + 2); by = __ldg(p6row + 3); cx = __ldg(p6row + 4); cy = __ldg(p6row + 5);
+    }
+    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
     float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
     int cnt = 0;
     for (int x = xs; x <= xe; ++x) {
@@ -1231,14 +1278,13 @@ __device__ __noinline__ float4 bwd_row_exact(const float* __restrict__ p6row, co
     return make_float4(M0, A1, A2, __int_as_float(cnt));
 }
 
-template <class ThreadStats, class WS>
+template <bool GATHER, class ThreadStats, class WS>
 __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S, float* gmus,
                                                    int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                    int lane, ThreadStats& st) {
     const bool queued = lane < nb;
     const int f = queued ? S.qface[lane] : 0;
     const long long bf = (long long)b * P.F + f;
-    const float2* pp = reinterpret_cast<const float2*>(P.p6 + bf * 6);
     float M0 = 0.0f, Ss = 0.0f, St = 0.0f;              // sum g, sum g*(x - ax), sum g*(y - ay) over the face's fragments
     float A1x = 0.0f, A2x = 0.0f;                       // sum g*k1, sum g*k2 of the rows that took the exact path
     typename ThreadStats::count_t nfrag{};
@@ -1248,14 +1294,12 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         int cx0 = 0, cy0 = 0, bw = 1, bh = 0;
         float ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0;
         if (queued) {
-            const short4 fb = __ldg(P.face_box + bf);
-            const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-            ax = va.x; ay = va.y; bx = vb.x; by = vb.y; cx = vc.x; cy = vc.y;
+            const short4 fb = unpack_box(__ldg(P.face_box + bf));
+            load_face_xy<GATHER>(P, b, f, bf, ax, ay, bx, by, cx, cy);
             cx0 = max((int)fb.x, tx0); cy0 = max((int)fb.y, ty0);
             bw = min((int)fb.z, tx1) - cx0 + 1;
             bh = min((int)fb.w, ty1) - cy0 + 1;
-            prefetch_l1(P.len3 + bf * 3);               // the epilogue's operands travel while the rows are walked
-            prefetch_l1(P.ff + bf);
+            if (!GATHER) prefetch_l1(P.len3 + bf * 3);    // the epilogue's operands travel while the rows are walked
         }
         __syncwarp();                                   // queue entries consumed
         if (lane == 0) st.visits++;
@@ -1315,7 +1359,9 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
                     // certain columns: [ceil(lo + din), floor(hi - din)], none when the row is in doubt
                     const int xsi = doubt ? 32 : __float2int_ru(lo + sb.din), xei = doubt ? -1 : __float2int_rd(hi - sb.din);
                     const int ry = cy0 - ty0 + r;
-                    const float4 e = bwd_row_exact(reinterpret_cast<const float*>(pp), S.acc + ry * TILE, (int)fs, (int)fe, xsi, xei, tx0, ty0 + ry);
+                    const float4* vtrow = GATHER ? P.vt + (long long)b * P.V : nullptr;
+                    const void* src = GATHER ? static_cast<const void*>(P.faces + 3 * (long long)f) : static_cast<const void*>(P.p6 + bf * 6);
+                    const float4 e = bwd_row_exact(src, vtrow, S.acc + ry * TILE, (int)fs, (int)fe, xsi, xei, tx0, ty0 + ry);
                     M0 += e.x; A1x += e.y; A2x += e.z; nfrag += (unsigned)__float_as_int(e.w);
                 }
             }
@@ -1323,12 +1369,11 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
     }
     st.cand += nfrag; st.frag += nfrag;
     if (queued && (M0 != 0.0f || Ss != 0.0f || St != 0.0f || A1x != 0.0f || A2x != 0.0f)) {
-        const float2 va = __ldg(pp), vb = __ldg(pp + 1), vc = __ldg(pp + 2);
-        const EdgeSetup es = edge_setup(va.x, va.y, vb.x, vb.y, vc.x, vc.y);
+        float ax, ay, bx, by, cx, cy, r0, r1, r2;
+        load_face<GATHER>(P, b, f, bf, ax, ay, bx, by, cx, cy, r0, r1, r2);
+        const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
         const int2 lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
-        const float* pl = P.len3 + bf * 3;
-        const float r0 = __ldg(pl), r1 = __ldg(pl + 1), r2 = __ldg(pl + 2);
-        float sgn = (__ldg(P.ff + bf) < 0.0f) ? -1.0f : 1.0f;         // diff_fp_for.cu:94-96
+        float sgn = (__ldg(reinterpret_cast<const short*>(P.face_box + bf)) < 0) ? -1.0f : 1.0f;   // diff_fp_for.cu:94-96 (unpack_box)
         if (lab.x == lab.y) sgn = -sgn;                               // :167-169
         // the k1 / k2 moments from sum g*(x - ax), sum g*(y - ay)  (k1 = q*s - n*t, k2 = m*t - p*s)
         const float A1 = fmaf(es.q, Ss, -(es.n * St)) + A1x, A2 = fmaf(es.m, St, -(es.p * Ss)) + A2x;
@@ -1413,13 +1458,15 @@ __device__ __forceinline__ void prefetch_record(const RasterParams& P, int* L, i
 }
 
 // 8 resident CTAs (64 registers); 9 CTAs at 56 registers was measured slower (5.06 -> 6.19 ms on config 3)
-template <bool STATS>
+template <bool STATS, bool GATHER>
 __global__ void __launch_bounds__(THREADS, 8)
 k_step_replay(const RasterParams P) {
     __shared__ ReplayCtaSmem C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* gmus = reinterpret_cast<float*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
+    asm volatile("mov.b32 %0, %0;" : "+r"(lane));            // pinned, see k_raster
     const int regions = P.regions_x * P.regions_y;
     const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
     const int rr = P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions);
@@ -1427,7 +1474,9 @@ k_step_replay(const RasterParams P) {
     if (bflag == 0) return;                                   // not recorded: k_raster<MODE_STEP> walks this region
     const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
     const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
-    ReplayWarpSmem& S = C.warp[warp];
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(&C.warp[warp]);     // pinned in a register, see k_raster
+    asm volatile("mov.b32 %0, %0;" : "+r"(sbase));
+    ReplayWarpSmem& S = *reinterpret_cast<ReplayWarpSmem*>(__cvta_shared_to_generic(sbase));
     ThreadStatsT<STATS> st;
     double loss_acc = 0.0;
     unsigned nvalid_acc = 0u;
@@ -1485,14 +1534,15 @@ k_step_replay(const RasterParams P) {
                 tt[k] = ok ? __ldg(P.target + o) : 0.0f;
             }
             // Pipeline, two records deep: while batch k is processed, record k+1 has landed — the data of its faces
-            // (pixel box, projected vertices, lengths, facing) is being pulled into L2 by prefetches — and record k+2 is
+            // (pixel box, projected vertices, lengths; in gather mode the box only: the vertex records are shared by six faces
+            // and mostly cached, and prefetching them costs a stall on the vertex ids — measured slower) is being pulled into L2 by prefetches — and record k+2 is
             // in flight.  The kernel is latency-bound on exactly these loads (ncu: 53 % of its stall samples were
             // long-scoreboard before); staging the face data in shared memory by cp.async instead was measured slower.
             auto stage_faces = [&](int fid, int n) {
                 if (lane < n) {
                     const long long bf = (long long)b * P.F + fid;
-                    prefetch_l2(P.face_box + bf); prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5);
-                    prefetch_l2(P.len3 + bf * 3); prefetch_l2(P.ff + bf);
+                    prefetch_l2(P.face_box + bf);
+                    if (!GATHER) { prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5); prefetch_l2(P.len3 + bf * 3); }
                 }
             };
             int nbatch = 0, next = -1, id = 0, slot = 0;
@@ -1532,7 +1582,7 @@ k_step_replay(const RasterParams P) {
                     stage_faces(id, nbatch);
                 }
                 __syncwarp();
-                process_batch_rows(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
+                process_batch_rows<GATHER>(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
                 if (!more) break;
             }
         }
@@ -1560,7 +1610,7 @@ k_step_replay(const RasterParams P) {
 // batches of every tile; MODE_STEP + LINKED is a replay-only kernel (no region lists, no queues) that skips
 // the regions the forward sweep could not record — those are done by the ordinary MODE_STEP kernel, launched
 // right after it with bmode == 2, which in turn skips the recorded ones.
-template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false>
+template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false, bool GATHER = false>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
     constexpr bool RECORD = LINKED && MODE == MODE_FWD;
@@ -1571,7 +1621,9 @@ k_raster(const RasterParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* gmus = reinterpret_cast<float*>(smem_raw);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
+    asm volatile("mov.b32 %0, %0;" : "+r"(lane));            // pinned like the shared-memory base below (S2R is slow to rebuild)
     const int regions = P.regions_x * P.regions_y;
     // CTA order: angle-major (neighbouring regions of one angle run together and share its face data in
     // L2), or region-major (all angles of a region together: the last CTAs of the launch are then the
@@ -1585,7 +1637,11 @@ k_raster(const RasterParams P) {
     const long long sidx = (long long)b * (P.nsr_x * P.nsr_y) + sry * P.nsr_x + srx;
     const int* super = P.slist + sidx * P.NC;
     const int nsuper = __ldg(P.scount + sidx);
-    WarpSmem& S = C.warp[warp];
+    // the warp's shared-memory base is pinned in a register (opaque to the compiler): at the 64-register cap ptxas
+    // otherwise rebuilds it from %tid / %cluster_ctarank (two S2R + four ALU instructions) at dozens of places in the hot loops
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(&C.warp[warp]);
+    asm volatile("mov.b32 %0, %0;" : "+r"(sbase));
+    WarpSmem& S = *reinterpret_cast<WarpSmem*>(__cvta_shared_to_generic(sbase));
     ThreadStatsT<STATS> st;
 
     constexpr bool K_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
@@ -1848,8 +1904,8 @@ k_raster(const RasterParams P) {
                     const int f = __shfl_sync(FULL, cid, src) * CHUNK + lane;
                     const int f2 = __shfl_sync(FULL, cid, max(src2, 0)) * CHUNK + lane;
                     short4 fb = make_short4(BOX_EMPTY_LO, BOX_EMPTY_LO, -1, -1), fb2 = fb;
-                    if (f < P.F) fb = __ldg(fbrow + f);
-                    if (src2 >= 0 && f2 < P.F) fb2 = __ldg(fbrow + f2);
+                    if (f < P.F) fb = unpack_box(__ldg(fbrow + f));
+                    if (src2 >= 0 && f2 < P.F) fb2 = unpack_box(__ldg(fbrow + f2));
                     const bool fh = box_overlap(fb, tx0, ty0, tx1, ty1);
                     const unsigned hm = __ballot_sync(FULL, fh);
                     if (lane == 0) st.hits += (hm != 0u);
@@ -1891,8 +1947,8 @@ k_raster(const RasterParams P) {
                 if (MODE == MODE_FRAG) process_batch<MODE, EXACT_DIV>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
                 else if (K_BWD) {
                     if (!prefix_ready) { build_row_prefix(S, lane); prefix_ready = true; }
-                    process_batch_rows(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
-                } else process_batch_blocked<MODE, EXACT_DIV, DIRECT>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                    process_batch_rows<GATHER>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                } else process_batch_blocked<MODE, EXACT_DIV, DIRECT, GATHER>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
                 if (!replay) {
                     const int rest = qn - nbatch;              // < 32: shift the tail to the front
                     int tf = 0;

@@ -175,6 +175,9 @@ k_vertex_transform(const VertexParams P, float4* __restrict__ vt) {
 // grid = (ceil(F / 256), B): a warp holds 32 consecutive faces of ONE angle, i.e. exactly one chunk of the
 // raster kernels, so the per-face pixel boxes and the chunk box (k_chunk_bbox's job at the Rasterizer
 // boundary) come out of the same pass while the projected vertices are still in registers.
+// FULL = false (gather mode of the raster kernels): only the boxes are written — the pixel box of every face, which
+// also carries the facing sign (pack_box), and the chunk boxes; p6 / len3 / ff are not materialised at all.
+template <bool FULL>
 __global__ void __launch_bounds__(256)
 k_face_assemble(const VertexParams P, const float4* __restrict__ vt, const int* __restrict__ labels2,
                 float* __restrict__ p6, float* __restrict__ len3, float* __restrict__ ff,
@@ -210,16 +213,18 @@ k_face_assemble(const VertexParams P, const float4* __restrict__ vt, const int* 
         }
         facing = __fadd_rn(__fadd_rn(__fmul_rn(rx, nx), __fmul_rn(ry, ny)), __fmul_rn(rz, nz));
     }
-    float2* o = reinterpret_cast<float2*>(p6 + gid * 6);
-    o[0] = make_float2(a.x, a.y); o[1] = make_float2(bb.x, bb.y); o[2] = make_float2(c.x, c.y);
-    len3[gid * 3 + 0] = a.z; len3[gid * 3 + 1] = bb.z; len3[gid * 3 + 2] = c.z;
-    ff[gid] = facing;
+    if (FULL) {
+        float2* o = reinterpret_cast<float2*>(p6 + gid * 6);
+        o[0] = make_float2(a.x, a.y); o[1] = make_float2(bb.x, bb.y); o[2] = make_float2(c.x, c.y);
+        len3[gid * 3 + 0] = a.z; len3[gid * 3 + 1] = bb.z; len3[gid * 3 + 2] = c.z;
+        ff[gid] = facing;
+    }
     const int2 lab = __ldg(reinterpret_cast<const int2*>(labels2) + f);
     int ix0, iy0, ix1, iy1;
     if (lab.x >= lab.y && face_int_bbox(a.x, a.y, bb.x, bb.y, c.x, c.y, P.H, P.W, ix0, iy0, ix1, iy1)) {   // as k_chunk_bbox
         x0 = ix0; y0 = iy0; x1 = ix1; y1 = iy1;
     }
-    face_box[gid] = make_short4((short)x0, (short)y0, (short)x1, (short)y1);
+    face_box[gid] = pack_box(x0, y0, x1, y1, facing < 0.0f);
     }
     // blockDim.x is a multiple of 32 and chunks start at multiples of 32: one warp == one chunk
     x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);

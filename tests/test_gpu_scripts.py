@@ -163,7 +163,8 @@ def test_ours_call_sequence(cuda_lib, optional_imports, tmp_path):
     assert len(rows) == args.niter and rows[0].startswith("~ 000 l2_loss: ") and " edge: " in rows[0] and " time: " in rows[0]
     l2 = [float(r.split("l2_loss:")[1].split()[0]) for r in rows]
     assert l2[-1] < 0.6 * l2[0], (l2[0], l2[-1])                                    # the loop optimises
-    assert log[0].startswith("@ statistics of mesh: 642, 1280")                     # icosphere(3) written by save_init_mesh, read back
+    # icosphere(3) written by save_init_mesh, read back (the "~ res_np" lines are written first: optimize.py:121 buffers the rest)
+    assert any(ln.startswith("@ statistics of mesh: 642, 1280") for ln in log)
     assert float(model.mus[0]) == 0.0 and float(model.mus[1]) > 0.5                  # mus[0] pinned to p_min (vanilla.py:148-149)
 
     # the refinement branch's mesh utilities (ours.py:82-97) on the optimised mesh: subdivide + save + reload as a template
