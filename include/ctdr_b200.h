@@ -36,8 +36,8 @@
 extern "C" {
 #endif
 
-#define CTDR_ABI_VERSION 3   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi; 3: + ctdr_launch_count,
-                                ctdr_project_residual_step_timed */
+#define CTDR_ABI_VERSION 4   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi; 3: + ctdr_launch_count,
+                                ctdr_project_residual_step_timed; 4: + the float64 instantiation (*_f64) */
 
 /* argument errors */
 #define CTDR_E_NULL      (-1)   /* a required pointer is NULL */
@@ -186,6 +186,41 @@ int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles,
                          int H, int W, double spacing_x, double spacing_y, double max_sino_val,
                          const float* grad_p6, const float* grad_len3,
                          float* grad_verts, ctdr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * float64 instantiation — the reference dispatches its kernels over float AND double
+ * (AT_DISPATCH_FLOATING_TYPES, diff_fp_for.cu:251, diff_fp_back.cu:326) and FP / Model take a dtype
+ * (fp_vecs.py:53-56, vanilla.py:27,31).  Same arguments as the float32 entry points with double
+ * arrays (geometry tables as float64: the float32 ProjectionAngles widened, Vectors as they are);
+ * same workspace (ctdr_raster_workspace_bytes).  Tile-binned like the float32 kernels, every pixel
+ * accumulated in ascending face order with IEEE divisions; the backward reduces three moments per
+ * (tile, face) and adds them with double atomics.  n_mus <= 2048.  This is the high-precision
+ * referee / drop-in for dtype=torch.float64, not the tuned path.
+ * ------------------------------------------------------------------------------------------- */
+int ctdr_raster_forward_f64(const double* p6, const double* ff, const double* len3,
+                            const int32_t* labels2, const double* mus, int n_mus,
+                            int B, int F, int H, int W, double max_sino_val,
+                            double* im, int32_t* cnt,
+                            void* workspace, size_t workspace_bytes,
+                            int64_t* stats, unsigned flags, ctdr_stream_t stream);
+int ctdr_raster_backward_f64(const double* grad_im, const double* im,
+                             const double* p6, const double* ff, const double* len3,
+                             const int32_t* labels2, const double* mus, int n_mus,
+                             int B, int F, int H, int W, double max_sino_val,
+                             double* grad_p6, double* grad_len3, double* grad_mus,
+                             void* workspace, size_t workspace_bytes,
+                             int64_t* stats, unsigned flags, ctdr_stream_t stream);
+int ctdr_vertex_forward_f64(int geom_kind, const double* geom, int nangles,
+                            const int64_t* idx_angles, int B,
+                            const double* verts, int V, const int32_t* faces, int F,
+                            int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                            double* p6, double* len3, double* ff, ctdr_stream_t stream);
+int ctdr_vertex_backward_f64(int geom_kind, const double* geom, int nangles,
+                             const int64_t* idx_angles, int B,
+                             const double* verts, int V, const int32_t* faces, int F,
+                             int H, int W, double spacing_x, double spacing_y, double max_sino_val,
+                             const double* grad_p6, const double* grad_len3,
+                             double* grad_verts, ctdr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused projector — mesh + geometry in, sinogram out; replaces FP.forward end to end

@@ -73,9 +73,11 @@ def main(rep, lib, src_path):
         return name
 
     # the two kernels of the residual step: forward (records batches) and the replay-only residual/backward
-    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1", "k_rasterILi0ELb0ELb0ELb0ELb1"),
+    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1, (bool)1", "k_rasterILi0ELb0ELb0ELb0ELb1ELb1"),
+                           ("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1>", "k_rasterILi0ELb0ELb0ELb0ELb1EE"),
                            ("k_raster<(int)3, (bool)0, (bool)0, (bool)0, (bool)1", "k_rasterILi3ELb0ELb0ELb0ELb1"),
-                           ("k_step_replay<(bool)0", "k_step_replayILb0E")):
+                           ("k_step_replay<(bool)0, (bool)1", "k_step_replayILb0ELb1"),
+                           ("k_step_replay<(bool)0>", "k_step_replayILb0EE")):
         try:
             blk = S.ncu_rows(rep, ksub_ncu)
         except SystemExit:

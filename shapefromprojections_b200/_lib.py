@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libctdr_b200.so")
 
 FLAG_NO_PREFILTER = 1
 FLAG_DETERMINISTIC = 2
-ABI_VERSION = 3          # include/ctdr_b200.h: CTDR_ABI_VERSION
+ABI_VERSION = 4          # include/ctdr_b200.h: CTDR_ABI_VERSION
 STAT_NONPOSITIVE_LEN, STAT_FRAGMENTS, STAT_CANDIDATES, STAT_LIST_SEGMENTS, STAT_COUNT = 0, 1, 2, 3, 8
 GEOM_PARALLEL3D, GEOM_PARALLEL3D_VEC, GEOM_CONE_VEC = 0, 1, 2
 GEOM_KINDS = {"parallel3d": GEOM_PARALLEL3D, "parallel3d_vec": GEOM_PARALLEL3D_VEC, "cone_vec": GEOM_CONE_VEC}
@@ -38,6 +38,10 @@ SIGNATURES = {
     "ctdr_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_vertex_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
     "ctdr_vertex_backward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "ctdr_raster_forward_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_raster_backward_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
+    "ctdr_vertex_forward_f64": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "ctdr_vertex_backward_f64": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
     "ctdr_project_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "ctdr_project_forward": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
                                   _vp, _vp, _vp, _sz, _vp, _u, _vp]),
@@ -132,9 +136,20 @@ def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")          # diff_fp.cpp:4
     if t.dtype != torch.float32:
-        raise TypeError(f"{name}: the B200 kernels are fp32 (got {t.dtype}); the fp64 instantiation of the "
-                        "reference is only available in the CPU oracle")
+        raise TypeError(f"{name}: this entry point is the float32 instantiation (got {t.dtype}); float64 runs through "
+                        "the staged operators (Rasterizer / FP(..., dtype=torch.float64, ...))")
     return t.contiguous()                                            # rasterizer.py:40-43
+
+
+def require_cuda_float(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    """float32 or float64 (AT_DISPATCH_FLOATING_TYPES, diff_fp_for.cu:251), CUDA, contiguous; ``dtype`` pins which."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")          # diff_fp.cpp:4
+    if t.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"{name} must be float32 or float64 (got {t.dtype})")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype} like the other operands (got {t.dtype})")
+    return t.contiguous()
 
 
 def require_numel(t: torch.Tensor, n: int, name: str) -> torch.Tensor:

@@ -4,6 +4,8 @@
 #include "../../include/ctdr_b200.h"
 #include "ctdr_raster.cuh"
 #include "ctdr_vertex.cuh"
+#include "ctdr_raster64.cuh"
+#include "ctdr_vertex64.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -764,6 +766,110 @@ int ctdr_vertex_backward(int geom_kind, const float* geom, int nangles, const in
     if (!geom || !idx_angles || !verts || !faces || !grad_p6 || !grad_len3 || !grad_verts) return fail(CTDR_E_NULL, "ctdr_vertex_backward: null pointer");
     const VertexParams P = vertex_params(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
     return launch_vertex_backward(P, grad_p6, grad_len3, grad_verts, stream);
+}
+
+// ---- float64 instantiation -------------------------------------------------------------------
+static int raster64_common(Raster64Params& P, const double* p6, const double* ff, const double* len3, const int32_t* labels2,
+                           const double* mus, int n_mus, int B, int F, int H, int W, double msv,
+                           void* workspace, size_t workspace_bytes, int64_t* stats, cudaStream_t stream, const char* who) {
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (n_mus > 2048) return fail(CTDR_E_SHAPE, "%s: n_mus=%d > 2048", who, n_mus);
+    if (!p6 || !ff || !len3 || !labels2 || !mus || !workspace) return fail(CTDR_E_NULL, "%s: null pointer", who);
+    RasterWs ws;
+    const size_t need = raster_ws_layout(B, F, H, W, false, false, &ws, workspace);
+    if (workspace_bytes < need) return fail(CTDR_E_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+    RasterParams D;                                          // the decomposition is the float32 kernels'
+    memset(&D, 0, sizeof(D));
+    D.B = B; D.F = F; D.H = H; D.W = W;
+    fill_decomposition(D, ws.boxes, ws.face_boxes, ws.slist, ws.scount);
+    memset(&P, 0, sizeof(P));
+    P.p6 = p6; P.ff = ff; P.len3 = len3; P.labels2 = labels2; P.mus = mus; P.n_mus = n_mus;
+    P.B = B; P.F = F; P.H = H; P.W = W; P.msv = msv;
+    P.NC = D.NC; P.RT = D.RT; P.regions_x = D.regions_x; P.regions_y = D.regions_y;
+    P.chunk_box = ws.boxes; P.face_box = ws.face_boxes; P.slist = ws.slist; P.scount = ws.scount;
+    P.nsr_x = D.nsr_x; P.nsr_y = D.nsr_y; P.sr_rx = D.sr_rx; P.sr_ry = D.sr_ry; P.region_major = D.region_major;
+    P.stats = reinterpret_cast<unsigned long long*>(stats);
+    const long long warps = (long long)B * P.NC;
+    const long long blocks = (warps + WARPS - 1) / WARPS;
+    if (blocks > 0x7fffffffLL || (long long)B * P.regions_x * P.regions_y > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    k_chunk_bbox64<<<(unsigned)blocks, THREADS, 0, stream>>>(p6, labels2, B, F, H, W, P.NC, ws.boxes, ws.face_boxes);
+    CTDR_LAUNCHED(1, "k_chunk_bbox64 launch");
+    return launch_chunk_bbox(D, ws.boxes, ws.face_boxes, stream, true);      // super-region lists from the chunk boxes
+}
+
+int ctdr_raster_forward_f64(const double* p6, const double* ff, const double* len3, const int32_t* labels2,
+                            const double* mus, int n_mus, int B, int F, int H, int W, double max_sino_val,
+                            double* im, int32_t* cnt, void* workspace, size_t workspace_bytes,
+                            int64_t* stats, unsigned flags, ctdr_stream_t stream) {
+    (void)flags;
+    if (!im) return fail(CTDR_E_NULL, "ctdr_raster_forward_f64: null pointer");
+    Raster64Params P;
+    if (int rc = raster64_common(P, p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, workspace, workspace_bytes, stats, stream, "ctdr_raster_forward_f64")) return rc;
+    P.im = im; P.cnt = cnt;
+    k_raster64<false><<<(unsigned)((long long)B * P.regions_x * P.regions_y), THREADS, 0, stream>>>(P);
+    CTDR_LAUNCHED(1, "k_raster64 launch");
+    return 0;
+}
+
+int ctdr_raster_backward_f64(const double* grad_im, const double* im, const double* p6, const double* ff, const double* len3,
+                             const int32_t* labels2, const double* mus, int n_mus, int B, int F, int H, int W, double max_sino_val,
+                             double* grad_p6, double* grad_len3, double* grad_mus, void* workspace, size_t workspace_bytes,
+                             int64_t* stats, unsigned flags, ctdr_stream_t stream) {
+    (void)flags;
+    if (!grad_im || !im || !grad_p6 || !grad_len3 || !grad_mus) return fail(CTDR_E_NULL, "ctdr_raster_backward_f64: null pointer");
+    Raster64Params P;
+    if (int rc = raster64_common(P, p6, ff, len3, labels2, mus, n_mus, B, F, H, W, max_sino_val, workspace, workspace_bytes, stats, stream, "ctdr_raster_backward_f64")) return rc;
+    P.grad_im = grad_im; P.im_in = im; P.grad_p6 = grad_p6; P.grad_len3 = grad_len3; P.grad_mus = grad_mus;
+    k_raster64<true><<<(unsigned)((long long)B * P.regions_x * P.regions_y), THREADS, (size_t)n_mus * sizeof(double), stream>>>(P);
+    CTDR_LAUNCHED(1, "k_raster64 launch");
+    return 0;
+}
+
+static Vertex64Params vertex64_params(int kind, const double* geom, int nangles, const int64_t* idx, int B, const double* verts, int V,
+                                      const int32_t* faces, int F, int H, int W, double sx, double sy, double msv) {
+    const VertexParams Q = vertex_params(kind, nullptr, nangles, idx, B, nullptr, V, faces, F, H, W, sx, sy, msv);
+    Vertex64Params P;
+    memset(&P, 0, sizeof(P));
+    P.kind = kind; P.geom = geom; P.idx_angles = reinterpret_cast<const long long*>(idx); P.nangles = nangles;
+    P.B = B; P.V = V; P.F = F; P.H = H; P.W = W; P.verts = verts; P.faces = faces;
+    P.msv = msv;
+    P.P00 = (double)Q.P00; P.P11 = (double)Q.P11; P.P13 = (double)Q.P13;     // the float32 matrix widened (fp_opengl.py:44-45)
+    return P;
+}
+
+int ctdr_vertex_forward_f64(int geom_kind, const double* geom, int nangles, const int64_t* idx_angles, int B,
+                            const double* verts, int V, const int32_t* faces, int F, int H, int W,
+                            double spacing_x, double spacing_y, double max_sino_val,
+                            double* p6, double* len3, double* ff, ctdr_stream_t stream) {
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, 1)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !p6 || !len3 || !ff) return fail(CTDR_E_NULL, "ctdr_vertex_forward_f64: null pointer");
+    const Vertex64Params P = vertex64_params(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    const long long blocks = ((long long)B * F + 255) / 256;
+    if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
+    k_vertex_forward64<<<(unsigned)blocks, 256, 0, stream>>>(P, p6, len3, ff);
+    CTDR_LAUNCHED(1, "k_vertex_forward64 launch");
+    return 0;
+}
+
+int ctdr_vertex_backward_f64(int geom_kind, const double* geom, int nangles, const int64_t* idx_angles, int B,
+                             const double* verts, int V, const int32_t* faces, int F, int H, int W,
+                             double spacing_x, double spacing_y, double max_sino_val,
+                             const double* grad_p6, const double* grad_len3, double* grad_verts, ctdr_stream_t stream) {
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, 1)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !grad_p6 || !grad_len3 || !grad_verts) return fail(CTDR_E_NULL, "ctdr_vertex_backward_f64: null pointer");
+    const Vertex64Params P = vertex64_params(geom_kind, geom, nangles, idx_angles, B, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+    int slices = 1;
+    const long long face_blocks = (F + 255) / 256;
+    while (slices < B && face_blocks * slices < 24 * 148 && slices < 64) slices <<= 1;
+    if (slices > B) slices = B;
+    const int per = (B + slices - 1) / slices;
+    k_vertex_backward64<<<dim3((unsigned)face_blocks, (unsigned)((B + per - 1) / per)), 256, 0, stream>>>(P, grad_p6, grad_len3, grad_verts, per);
+    CTDR_LAUNCHED(1, "k_vertex_backward64 launch");
+    return 0;
 }
 
 size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_backward) {

@@ -24,7 +24,7 @@ def _check(t, name, dtype=None):
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")              # diff_fp.cpp:5
     if dtype is not None and t.dtype != dtype:
-        raise TypeError(f"{name} must be {dtype} on the B200 kernels (got {t.dtype})")
+        raise TypeError(f"{name} must be {dtype} like points2d (got {t.dtype})")
 
 
 def _dim(t, shape, msg):
@@ -37,10 +37,13 @@ def forward(points2d_bxfx6, pointsdirect_bxfx1, pointsbbox_bxfx4, pointslen_bxfx
             is_the_first_pass, max_sino_val):
     """``dr_forward_batch`` (``diff_fp.cpp:21-67``).  ``pointsbbox_bxfx4`` is validated but not read:
     the kernels derive the bounding boxes from ``points2d`` themselves (same values, rasterizer.py:23-32)."""
+    dt = points2d_bxfx6.dtype                     # AT_DISPATCH_FLOATING_TYPES(points2d.type(), ...) (diff_fp_for.cu:251)
+    if dt not in (torch.float32, torch.float64):
+        raise TypeError(f"points2d_bxfx6 must be float32 or float64 (got {dt})")
     for t, n in ((points2d_bxfx6, "points2d_bxfx6"), (pointsdirect_bxfx1, "pointsdirect_bxfx1"),
                  (pointsbbox_bxfx4, "pointsbbox_bxfx4"), (pointslen_bxfx3, "pointslen_bxfx3"),
                  (mus_n, "mus_n"), (im_bxhxwx1, "im_bxhxwx1")):
-        _check(t, n, torch.float32)
+        _check(t, n, dt)
     _check(labels_fx2, "labels_fx2", torch.int32)
     _check(cntvisible_bxhxwx1, "cntvisible_bxhxwx1", torch.int32)
     _check(firstidx_bxhxwx1, "firstidx_bxhxwx1")
@@ -59,13 +62,17 @@ def forward(points2d_bxfx6, pointsdirect_bxfx1, pointsbbox_bxfx4, pointslen_bxfx
     with torch.cuda.device(dev):
         if is_the_first_pass:
             ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
-            rc = L.ctdr_raster_forward(points2d_bxfx6.data_ptr(), pointsdirect_bxfx1.data_ptr(),
+            entry = L.ctdr_raster_forward if dt == torch.float32 else L.ctdr_raster_forward_f64
+            rc = entry(points2d_bxfx6.data_ptr(), pointsdirect_bxfx1.data_ptr(),
                                        pointslen_bxfx3.data_ptr(), labels_fx2.data_ptr(), mus_n.data_ptr(),
                                        mus_n.numel(), B, F, H, W, float(max_sino_val), im_bxhxwx1.data_ptr(),
                                        cntvisible_bxhxwx1.data_ptr(), ws.data_ptr(), ws.numel(), None, 0,
                                        _lib.stream_ptr(dev))
             _lib.check(rc, "ctdr_raster_forward")
         else:
+            if dt != torch.float32:
+                raise TypeError("pass 2 (the CSR fragment list) exists in float32 only here: it is a parity/debug output, "
+                                "the backward recomputes coverage (DESIGN.md)")
             _check(imwei_3vf, "imwei_3vf", torch.float32)
             _check(imidx_vf, "imidx_vf", torch.int32)
             if firstidx_bxhxwx1.dtype != torch.int32 or firstidx_bxhxwx1.numel() != B * H * W:
@@ -85,11 +92,14 @@ def backward(grad_sino_bxhxwxd, image_bxhxwxd, imidx_vf, cntvisible_bxhxwx1, fir
              points2d_bxfx6, len_bxfx3, labels_fx2, mus_n, front_facing_bxfx1,
              grad_points2d_bxfx6, grad_len_bxfx3, grad_mus_n):
     """``dr_backward_batch`` (``diff_fp.cpp:77-129``); accumulates into the three ``grad_*`` tensors."""
+    dt = grad_sino_bxhxwxd.dtype                  # diff_fp_back.cu:326 dispatches float and double
+    if dt not in (torch.float32, torch.float64):
+        raise TypeError(f"grad_sino_bxhxwxd must be float32 or float64 (got {dt})")
     for t, n in ((grad_sino_bxhxwxd, "grad_sino_bxhxwxd"), (image_bxhxwxd, "image_bxhxwxd"),
                  (points2d_bxfx6, "points2d_bxfx6"), (len_bxfx3, "len_bxfx3"), (mus_n, "mus_n"),
                  (front_facing_bxfx1, "front_facing_bxfx1"), (grad_points2d_bxfx6, "grad_points2d_bxfx6"),
                  (grad_len_bxfx3, "grad_len_bxfx3"), (grad_mus_n, "grad_mus_n")):
-        _check(t, n, torch.float32)
+        _check(t, n, dt)
     for t, n in ((imidx_vf, "imidx_vf"), (cntvisible_bxhxwx1, "cntvisible_bxhxwx1"),
                  (firstidx_bxhxwx1, "firstidx_bxhxwx1"), (imwei_3vf, "imwei_3vf")):
         _check(t, n)
@@ -117,7 +127,8 @@ def backward(grad_sino_bxhxwxd, image_bxhxwxd, imidx_vf, cntvisible_bxhxwx1, fir
         grad = grad_sino_bxhxwxd * recorded.reshape(B, H, W, 1).to(grad_sino_bxhxwxd.dtype)
     with torch.cuda.device(dev):
         ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
-        rc = L.ctdr_raster_backward(grad.data_ptr(), image_bxhxwxd.data_ptr(), points2d_bxfx6.data_ptr(),
+        entry = L.ctdr_raster_backward if dt == torch.float32 else L.ctdr_raster_backward_f64
+        rc = entry(grad.data_ptr(), image_bxhxwxd.data_ptr(), points2d_bxfx6.data_ptr(),
                                     front_facing_bxfx1.data_ptr(), len_bxfx3.data_ptr(), labels_fx2.data_ptr(),
                                     mus_n.data_ptr(), mus_n.numel(), B, F, H, W, msv,
                                     grad_points2d_bxfx6.data_ptr(), grad_len_bxfx3.data_ptr(), grad_mus_n.data_ptr(),

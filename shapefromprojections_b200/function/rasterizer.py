@@ -34,10 +34,11 @@ def raster_forward(p6, len3, ff, labels, mus, H, W, max_sino_val, *, want_cnt=Fa
 
     Returns ``(im [B,H,W,1], cnt [B,H,W,1] int32 | None, stats int64[8] | None)``.
     """
-    p6 = _lib.require_cuda_f32(p6, "p_bxfx6")
-    len3 = _lib.require_cuda_f32(len3, "len_bxfx3")
-    ff = _lib.require_cuda_f32(ff, "front_facing_bxfx1")
-    mus = _lib.require_cuda_f32(mus, "mus_n")
+    p6 = _lib.require_cuda_float(p6, "p_bxfx6")
+    dt = p6.dtype                                     # float32 or float64 (diff_fp_for.cu:251 dispatches both)
+    len3 = _lib.require_cuda_float(len3, "len_bxfx3", dt)
+    ff = _lib.require_cuda_float(ff, "front_facing_bxfx1", dt)
+    mus = _lib.require_cuda_float(mus, "mus_n", dt)
     if labels.dtype != dtype_int or not labels.is_cuda:
         raise RuntimeError("labels_fx2 must be a CUDA int32 tensor")
     labels = labels.contiguous()
@@ -47,15 +48,16 @@ def raster_forward(p6, len3, ff, labels, mus, H, W, max_sino_val, *, want_cnt=Fa
     dev = p6.device
     stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.int64, device=dev) if want_stats else None
     if B == 0 or F == 0:        # empty mesh / no angles: the reference's loops run zero times
-        return (torch.zeros(B, H, W, 1, dtype=torch.float32, device=dev),
+        return (torch.zeros(B, H, W, 1, dtype=dt, device=dev),
                 torch.zeros(B, H, W, 1, dtype=dtype_int, device=dev) if want_cnt else None, stats)
-    im = torch.empty(B, H, W, 1, dtype=torch.float32, device=dev)
+    im = torch.empty(B, H, W, 1, dtype=dt, device=dev)
     cnt = torch.empty(B, H, W, 1, dtype=dtype_int, device=dev) if want_cnt else None
     L = _lib.lib()
     nbytes = L.ctdr_raster_workspace_bytes(B, F, H, W)
     ws = _lib.workspace(dev, nbytes)
+    entry = L.ctdr_raster_forward if dt == torch.float32 else L.ctdr_raster_forward_f64
     with torch.cuda.device(dev):
-        rc = L.ctdr_raster_forward(p6.data_ptr(), ff.data_ptr(), len3.data_ptr(), labels.data_ptr(), mus.data_ptr(),
+        rc = entry(p6.data_ptr(), ff.data_ptr(), len3.data_ptr(), labels.data_ptr(), mus.data_ptr(),
                                    mus.numel(), B, F, H, W, float(max_sino_val), im.data_ptr(), _lib.ptr(cnt),
                                    ws.data_ptr(), ws.numel(), _lib.ptr(stats),
                                    default_flags() if flags is None else flags, _lib.stream_ptr(dev))
@@ -68,7 +70,7 @@ def raster_backward(grad_im, im, p6, len3, ff, labels, mus, max_sino_val, *, fla
     B, F = p6.shape[0], p6.shape[1]
     H, W = im.shape[1], im.shape[2]
     dev = p6.device
-    grad_im = _lib.require_cuda_f32(grad_im, "dldI_bxhxwx1")
+    grad_im = _lib.require_cuda_float(grad_im, "dldI_bxhxwx1", p6.dtype)
     dldp = torch.zeros_like(p6)                                    # rasterizer.py:97-99
     dldf = torch.zeros_like(len3)
     dldmu = torch.zeros_like(mus)
@@ -77,8 +79,9 @@ def raster_backward(grad_im, im, p6, len3, ff, labels, mus, max_sino_val, *, fla
         return (dldp, dldf, dldmu, stats) if want_stats else (dldp, dldf, dldmu)
     L = _lib.lib()
     ws = _lib.workspace(dev, L.ctdr_raster_workspace_bytes(B, F, H, W))
+    entry = L.ctdr_raster_backward if p6.dtype == torch.float32 else L.ctdr_raster_backward_f64
     with torch.cuda.device(dev):
-        rc = L.ctdr_raster_backward(grad_im.data_ptr(), im.data_ptr(), p6.data_ptr(), ff.data_ptr(), len3.data_ptr(),
+        rc = entry(grad_im.data_ptr(), im.data_ptr(), p6.data_ptr(), ff.data_ptr(), len3.data_ptr(),
                                     labels.data_ptr(), mus.data_ptr(), mus.numel(), B, F, H, W, float(max_sino_val),
                                     dldp.data_ptr(), dldf.data_ptr(), dldmu.data_ptr(), ws.data_ptr(), ws.numel(),
                                     _lib.ptr(stats), default_flags() if flags is None else flags,
@@ -130,6 +133,16 @@ class GeometryDevice:
             table = torch.tensor(proj_geom["Vectors"], dtype=torch.float32)         # :64
         self.table = table.contiguous().to(device)
         self.nangles = int(self.table.shape[0])
+        self._table64 = None
+        self._source = proj_geom["ProjectionAngles"] if self.kind == _lib.GEOM_PARALLEL3D else proj_geom["Vectors"]
+
+    @property
+    def table64(self):
+        """The geometry table as the reference builds it for ``dtype=torch.float64`` (``torch.tensor(..., dtype=dtype)``:
+        the float32 ProjectionAngles widened, the float64 Vectors as they are)."""
+        if self._table64 is None:
+            self._table64 = torch.tensor(self._source, dtype=torch.float64).contiguous().to(self.table.device)
+        return self._table64
 
 
 _adjacency_cache: dict = {}       # (data_ptr, F, version, V) -> (faces tensor kept alive, start, corner); a few meshes
@@ -193,16 +206,19 @@ def _check_mesh(geom, verts, faces_i32, labels, mus, idx):
 
 def vertex_forward(geom: GeometryDevice, verts, faces_i32, idx_angles):
     """p_bxfx6, len_bxfx3, front_facing_bxfx1 exactly as the reference FP modules build them."""
-    verts = _lib.require_cuda_f32(verts, "verts_vx3")
+    verts = _lib.require_cuda_float(verts, "verts_vx3")
     faces_i32 = _lib.require_cuda_i32(faces_i32, "faces_fx3")
     dev = verts.device
     idx = _device_idx(idx_angles, dev, geom.nangles)
     B, V, F = idx.numel(), verts.shape[0], faces_i32.shape[0]
-    p6 = torch.empty(B, F, 6, dtype=torch.float32, device=dev)
-    len3 = torch.empty(B, F, 3, dtype=torch.float32, device=dev)
-    ff = torch.empty(B, F, 1, dtype=torch.float32, device=dev)
+    f64 = verts.dtype == torch.float64
+    p6 = torch.empty(B, F, 6, dtype=verts.dtype, device=dev)
+    len3 = torch.empty(B, F, 3, dtype=verts.dtype, device=dev)
+    ff = torch.empty(B, F, 1, dtype=verts.dtype, device=dev)
+    table = geom.table64 if f64 else geom.table
+    entry = _lib.lib().ctdr_vertex_forward_f64 if f64 else _lib.lib().ctdr_vertex_forward
     with torch.cuda.device(dev):
-        rc = _lib.lib().ctdr_vertex_forward(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(), B,
+        rc = entry(geom.kind, table.data_ptr(), geom.nangles, idx.data_ptr(), B,
                                             verts.data_ptr(), V, faces_i32.data_ptr(), F, geom.H, geom.W,
                                             geom.spacing_x, geom.spacing_y, float(geom.max_sino_val),
                                             p6.data_ptr(), len3.data_ptr(), ff.data_ptr(), _lib.stream_ptr(dev))
@@ -226,11 +242,14 @@ class VertexStage(Function):
         verts, faces_i32, idx = ctx.saved_tensors
         geom = ctx.geom
         dev = verts.device
-        gp6 = _lib.require_cuda_f32(gp6, "grad p6")
-        glen3 = _lib.require_cuda_f32(glen3, "grad len3")
+        gp6 = _lib.require_cuda_float(gp6, "grad p6", verts.dtype)
+        glen3 = _lib.require_cuda_float(glen3, "grad len3", verts.dtype)
         gverts = torch.zeros_like(verts)
+        f64 = verts.dtype == torch.float64
+        table = geom.table64 if f64 else geom.table
+        entry = _lib.lib().ctdr_vertex_backward_f64 if f64 else _lib.lib().ctdr_vertex_backward
         with torch.cuda.device(dev):
-            rc = _lib.lib().ctdr_vertex_backward(geom.kind, geom.table.data_ptr(), geom.nangles, idx.data_ptr(),
+            rc = entry(geom.kind, table.data_ptr(), geom.nangles, idx.data_ptr(),
                                                  idx.numel(), verts.data_ptr(), verts.shape[0], faces_i32.data_ptr(),
                                                  faces_i32.shape[0], geom.H, geom.W, geom.spacing_x, geom.spacing_y,
                                                  float(geom.max_sino_val), gp6.data_ptr(), glen3.data_ptr(),

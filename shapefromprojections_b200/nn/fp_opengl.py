@@ -18,5 +18,5 @@ class FP(_ProjectorBase):
         if proj_geom["type"] != "parallel3d":
             raise ValueError("fp_opengl.FP expects type 'parallel3d', got " + str(proj_geom["type"]))
         super().__init__(proj_geom, labels, dtype, fused)
-        self.angles = self.geom.table                                            # fp_opengl.py:63
+        self.angles = self.geom.table64 if dtype == torch.float64 else self.geom.table   # fp_opengl.py:63
         self.P = torch.tensor(compute_P(proj_geom), dtype=dtype, device=self.angles.device)  # :44-45

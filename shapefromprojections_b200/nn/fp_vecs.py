@@ -38,8 +38,10 @@ class _ProjectorBase(nn.Module):
 
     def __init__(self, proj_geom, labels, dtype=torch.float32, fused=True):
         super().__init__()
-        if dtype != torch.float32:
-            raise TypeError("the B200 projector is fp32; use the CPU oracle for the fp64 instantiation")
+        if dtype not in (torch.float32, torch.float64):
+            raise TypeError(f"FP: dtype must be torch.float32 or torch.float64 (got {dtype})")
+        if dtype == torch.float64:
+            fused = False      # float64 is the staged path (vertex stage -> Rasterizer), both in double on the device
         if not torch.cuda.is_available():
             raise RuntimeError("the B200 projector needs a CUDA device (there is no CPU fallback)")
         self.proj_geom = proj_geom
@@ -70,6 +72,8 @@ class _ProjectorBase(nn.Module):
         if mus_n.numel() <= self._label_max:
             raise IndexError(f"mus_n has {mus_n.numel()} entries but the face labels go up to {self._label_max}")
         faces32 = self._faces32(faces_fx3)
+        if self.dtype == torch.float64 and (verts_vx3.dtype != torch.float64 or mus_n.dtype != torch.float64):
+            raise TypeError("FP(dtype=torch.float64) expects float64 vertices and attenuations (Model(..., dtype=torch.float64))")
         if self.fused:
             im = ProjectMesh.apply(verts_vx3, mus_n, faces32, self.labels_fx2, idx_angles, self.geom, backprop)
         else:
@@ -89,8 +93,9 @@ class _ProjectorBase(nn.Module):
         obtains from 2-3 full renders plus torch reductions."""
         from ..function.rasterizer import _device_idx
         idx = _device_idx(idx_angles, self.labels_fx2.device, self.geom.nangles)
-        im, A, rhs, _ = project_forward_multi(self.geom, verts_vx3.detach().contiguous(), self._faces32(faces_fx3),
-                                              self.labels_fx2, mus_kxn, idx, target=target, want_gram=True)
+        # float32 kernels also for a float64 model: the normal equations are accumulated in float64 either way
+        im, A, rhs, _ = project_forward_multi(self.geom, verts_vx3.detach().to(torch.float32).contiguous(), self._faces32(faces_fx3),
+                                              self.labels_fx2, mus_kxn.to(torch.float32), idx, target=target, want_gram=True)
         return im, A, rhs
 
 
@@ -101,7 +106,7 @@ class FP(_ProjectorBase):
         if proj_geom["type"] not in ("parallel3d_vec", "cone_vec"):
             raise ValueError("fp_vecs.FP expects a *_vec geometry, got " + str(proj_geom["type"]))
         super().__init__(proj_geom, labels, dtype, fused)
-        self.vecs = self.geom.table                                              # fp_vecs.py:64
+        self.vecs = self.geom.table64 if dtype == torch.float64 else self.geom.table   # fp_vecs.py:64
         self.det_pos = self.vecs[:, 3:6]                                         # :72-74
         if proj_geom["type"] == "parallel3d_vec":
             self.det_pos = -self.max_sino_val * self.vecs[:, 0:3]
