@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libctdr_b200.so")
+LIB_PATH = os.environ.get("CTDR_LIB") or os.path.join(_HERE, "csrc", "libctdr_b200.so")   # CTDR_LIB: A/B builds (tools/)
 
 FLAG_NO_PREFILTER = 1
 FLAG_DETERMINISTIC = 2

@@ -644,6 +644,12 @@ int deterministic_window(RasterParams P, const VertexParams& VP, const ProjectWs
 extern "C" {
 
 int ctdr_abi_version(void) { return CTDR_ABI_VERSION; }
+#ifdef CTDR_PROBE_ROWSTATS
+int ctdr_debug_rowstats(unsigned long long* out4, int reset) {
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; return (int)cudaMemcpyToSymbol(ctdr::g_rowstats, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out4, ctdr::g_rowstats, 4 * sizeof(unsigned long long));
+}
+#endif
 
 int ctdr_selftest_quotient(unsigned long long samples, unsigned seed, unsigned long long* mismatches, ctdr_stream_t stream) {
     if (!mismatches) return fail(CTDR_E_NULL, "ctdr_selftest_quotient: null pointer");

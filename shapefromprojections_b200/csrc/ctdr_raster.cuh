@@ -1144,6 +1144,9 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
 // Faces without usable bounds (zero area, NaN, huge, two near-horizontal edges) and knife-edge rows on a
 // near-horizontal edge test every bounding-box pixel exactly.
 // ------------------------------------------------------------------------------------------
+#ifdef CTDR_PROBE_ROWSTATS
+__device__ unsigned long long g_rowstats[4];
+#endif
 constexpr int PREFIX_STRIDE = TILE + 1;
 // The prefix sums are kept in float64: a span sum is a DIFFERENCE of two prefixes, and with fp32 prefixes its
 // error would be an ulp of the whole row's running sum (measured: 2e-4 relative on grad_p6, the moments then
@@ -1195,8 +1198,29 @@ struct SpanSetupB {
                          // edges); the first / last row when it lies within rounding of a near-horizontal edge
 };
 
-// t_first / t_last: y - ay of the first and last row of the face in this tile (nrows rows); smax: max |x - ax|
-__device__ __forceinline__ SpanSetupB span_setup_bwd(const EdgeSetup& es, float t_first, float t_last, int nrows, float smax) {
+// t_first / t_last: y - ay of the first and last row of the face in this tile (nrows rows); smax: max |x - ax| over the
+// face's columns in this tile; axr = ax - tile origin: the bounds come out TILE-RELATIVE, so their own rounding is that
+// of numbers of tile size, not of detector size.
+//
+// Margin of edge j (in pixels, both sides of the estimated root).  The reference decides on COMPUTED values:
+// sign(k1), sign(k2) (edges 0, 1) and w0 = fl(fl(1 - w1) - w2) >= 0 (edge 2), with k1 = fma(s, q, -fl(n*t)),
+// k2 = fma(m, t, -fl(s*p)), s = fl(x - ax), t = fl(y - ay), w = fl32(k/d).  Against the exact line a_j*(x - root), with
+// u = 2^-24 = 6e-8 (s and t carry ONE rounding of their own magnitude — the difference is formed exactly, then rounded):
+//   edge 0 (a = q):    |k1 - exact| <= u*(|q|*|s| + 2*|n|*|t|)                        -> u*(smax + 2*|R_0|*tmax) pixels
+//   edge 1 (a = p):    |k2 - exact| <= u*(2*|p|*|s| + |m|*|t|)                        -> u*(2*smax + |R_1|*tmax) pixels
+//   edge 2 (a = q-p):  both of the above, over |q - p|, plus the float32 roundings of k1, k2 (now of size |d|), of w1,
+//                      w2 and of the two subtractions, 6u in barycentric units = 6u*|C_2| pixels (C_2 = |k3| / a_2)
+//                                                        -> u*((|q|+2|p|)*smax + (2|n|+|m|)*tmax)/|q-p| + 6u*|C_2| pixels
+//   this estimate:     1/a_j from MUFU.RCP and two products (4e-7 relative on R_j*t and C_j), and the roundings of
+//                      axr + C -/+ margin and of the fma (1.2e-7 each, of |axr| + |C_j| + |R_j|*tmax)
+//                                                        -> 5.2e-7*(|R_j|*tmax + |C_j|) + 2.4e-7*|axr| pixels
+// (|R_2|*tmax <= (2|n|+|m|)*tmax/|q-p|.)  The margins used are at least twice these bounds, plus a constant floor:
+//   margin_j = 2e-5 + 5e-7*|axr| + 4.8e-7*smax + (1.3e-6*T_j + 4.8e-7*S_j)/|a_j| + 3e-6*|C_j|
+//   T_0 = |n|*tmax, T_1 = |m|*tmax, T_2 = (2|n|+|m|)*tmax;  S_0 = S_1 = 0, S_2 = (|q|+2|p|)*smax.
+// (First version: one margin 1e-4 + 8e-6*(|C| + |R|*tmax) + 1e-6*|ax| for all edges of a face: 0.34 % of the (face, row)
+// pairs of config 3 took the exact path, 0.24 % with these; separate inner margins for the lower and the upper bound
+// bring it to 0.13 % but cost a register in the row loop and were measured slower.)
+__device__ __forceinline__ SpanSetupB span_setup_bwd(const EdgeSetup& es, float axr, float t_first, float t_last, int nrows, float smax) {
     SpanSetupB B;
     B.sp = {0.0f, -3.0e38f, 0.0f, -3.0e38f, 0.0f, 3.0e38f, 0.0f, 3.0e38f};
     const float tmax = fmaxf(fabsf(t_first), fabsf(t_last));
@@ -1205,28 +1229,33 @@ __device__ __forceinline__ SpanSetupB span_setup_bwd(const EdgeSetup& es, float 
     const float a[3] = {sg * es.q, -sg * es.p, -sg * (es.q - es.p)};
     const float beta[3] = {-sg * es.n, sg * es.m, -sg * (es.m - es.n)};
     const float gamma[3] = {0.0f, 0.0f, fabsf(es.k3)};
+    const float an = fabsf(es.n), am = fabsf(es.m);
+    const float TS[3] = {1.3e-6f * an * tmax, 1.3e-6f * am * tmax,
+                         1.3e-6f * (2.0f * an + am) * tmax + 4.8e-7f * (fabsf(es.q) + 2.0f * fabsf(es.p)) * smax};
+    const float mbase = 2e-5f + 5e-7f * fabsf(axr) + 4.8e-7f * smax;
     bool have_l = false, have_u = false;
-    float mmax = 0.0f;
+    float mmax_l = 0.0f, mmax_u = 0.0f;
     int nflat = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const bool use = fabsf(a[j]) > 1e-4f;
         const float ia = use ? __fdividef(1.0f, a[j]) : 0.0f;
         const float R = -beta[j] * ia, C = -gamma[j] * ia;
-        const float margin = 1e-4f + 8e-6f * (fabsf(C) + fabsf(R) * tmax) + 1e-6f * fabsf(es.ax);
+        const float margin = mbase + TS[j] * fabsf(ia) + 3e-6f * fabsf(C);
         const bool lower = use && a[j] > 0.0f, upper = use && a[j] < 0.0f;
-        const float cl = es.ax + C - margin, cu = es.ax + C + margin;
+        const float cl = axr + C - margin, cu = axr + C + margin;
         if (lower && !have_l) { B.sp.RL0 = R; B.sp.CL0 = cl; } else if (lower) { B.sp.RL1 = R; B.sp.CL1 = cl; }
         if (upper && !have_u) { B.sp.RU0 = R; B.sp.CU0 = cu; } else if (upper) { B.sp.RU1 = R; B.sp.CU1 = cu; }
         have_l |= lower; have_u |= upper;
-        if (use) mmax = fmaxf(mmax, margin);
-        else {
+        if (lower) mmax_l = fmaxf(mmax_l, margin);
+        if (upper) mmax_u = fmaxf(mmax_u, margin);
+        if (!use) {
             ++nflat;
             fb = beta[j]; fg = gamma[j];
             fthr = fabsf(a[j]) * smax + 1e-5f * (fabsf(beta[j]) * tmax + fabsf(gamma[j])) + 1e-30f;
         }
     }
-    B.din = 2.0f * mmax;
+    B.din = 2.0f * fmaxf(mmax_l, mmax_u);     // one value for both sides: a second live register in the row loop costs more than it saves (measured)
     // A near-horizontal edge is the top or the bottom of the triangle, so the rows of the bounding box lie on its
     // inner side; only the first or the last row can come within rounding of it (the value is linear in t).
     const float ak3 = fabsf(es.k3);
@@ -1305,14 +1334,13 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         if (lane == 0) st.visits++;
         const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
         const int x_hi = cx0 + bw - 1;
-        const SpanSetupB sb = span_setup_bwd(es, (float)cy0 - es.ay, (float)(cy0 + bh - 1) - es.ay, bh,
-                                             fmaxf(fabsf((float)cx0 - es.ax), fabsf((float)x_hi - es.ax)));
         // everything below in tile-relative coordinates (columns 0..15, rows 0..15)
         const float axr = es.ax - (float)tx0;
+        const SpanSetupB sb = span_setup_bwd(es, axr, (float)cy0 - es.ay, (float)(cy0 + bh - 1) - es.ay, bh,
+                                             fmaxf(fabsf((float)cx0 - es.ax), fabsf((float)x_hi - es.ax)));
         const double axd = (double)axr;
         const float xlo = (float)(cx0 - tx0), xhi = (float)(x_hi - tx0);
-        const float cl0 = sb.sp.CL0 - (float)tx0, cl1 = sb.sp.CL1 - (float)tx0;
-        const float cu0 = sb.sp.CU0 - (float)tx0, cu1 = sb.sp.CU1 - (float)tx0;
+        const float cl0 = sb.sp.CL0, cl1 = sb.sp.CL1, cu0 = sb.sp.CU0, cu1 = sb.sp.CU1;
         const double* E0 = prefix_e0(S);
         const int bhmax = __reduce_max_sync(FULL, bh);
         const float t0 = (float)cy0 - es.ay;            // y - ay of the face's first row in this tile
@@ -1320,16 +1348,22 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
         unsigned exact_rows = 0u;                       // rows left to the exact path below (kept out of the hot loop:
                                                         // a call inside it would force spills around every iteration)
         {
-            float t = t0;
+            float rf = 0.0f;
             int rowbase = rowbase0;
 #pragma unroll 1
-            for (int r = 0; r < bhmax; ++r, t += 1.0f, rowbase += PREFIX_STRIDE) {
+            for (int r = 0; r < bhmax; ++r, rf += 1.0f, rowbase += PREFIX_STRIDE) {
+                const float t = t0 + rf;                // one rounding, like the reference's own t = fl(y - ay): no drift over the rows
                 if (r < bh) {
                     const float lo = fmaxf(fmaf(sb.sp.RL0, t, cl0), fmaf(sb.sp.RL1, t, cl1));
                     const float hi = fminf(fmaf(sb.sp.RU0, t, cu0), fmaf(sb.sp.RU1, t, cu1));
                     const float fs = ceilf(fmaxf(lo, xlo)), fe = floorf(fminf(hi, xhi));   // candidate columns of this row
                     // the reference's exact test must decide: the row ends when a pixel centre lies within the margin
                     // of an edge; the whole bounding-box row when the row is in doubt (see SpanSetupB::doubt)
+#ifdef CTDR_PROBE_ROWSTATS      // diagnostic build only (tools/): how many (face, row) pairs take the exact path, and why
+                    atomicAdd(&g_rowstats[0], 1ull);
+                    if ((sb.doubt >> r) & 1u) atomicAdd(&g_rowstats[1], 1ull);
+                    else if ((fs - lo < sb.din) | (hi - fe < sb.din)) { atomicAdd(&g_rowstats[2], 1ull); if (fs > fe) atomicAdd(&g_rowstats[3], 1ull); }
+#endif
                     if (((sb.doubt >> r) & 1u) | (fs - lo < sb.din) | (hi - fe < sb.din)) {
                         exact_rows |= 1u << r;
                     } else if (fs <= fe) {

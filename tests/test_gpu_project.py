@@ -185,7 +185,11 @@ def test_fp_modules_surface(cuda_lib, kind):
     assert one.shape == (fp.height, fp.width)            # phat.squeeze() drops B == 1 (fp_vecs.py:203)
     assert torch.equal(one, phat[2].detach())
     with pytest.raises(TypeError):
-        FP(geom, lab, torch.float64)
+        FP(geom, lab, torch.float16)                         # float and double only, like AT_DISPATCH_FLOATING_TYPES (diff_fp_for.cu:251)
+    fp64 = FP(geom, lab, torch.float64)                      # the float64 instantiation: staged path in double (tests/test_gpu_f64.py)
+    assert fp64.fused is False and fp64.dtype == torch.float64
+    with pytest.raises(TypeError):
+        fp64.forward(v, faces64, idx_cpu, m)                 # float32 operands into a float64 projector
 
 
 @pytest.mark.parametrize("kind", list(GEOMS))
