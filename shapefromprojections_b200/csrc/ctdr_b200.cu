@@ -80,7 +80,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // behaviour does not follow ambient changes of the environment behind the caller's back.
 struct Tuning {
     int region_tiles = 0;        // CTDR_REGION_TILES: 2, 4 or 8; 0 = heuristic
-    int region_major = 1;        // CTDR_REGION_MAJOR: CTA order of k_raster (measured: 1 wins)
+    int region_major = 2;        // CTDR_REGION_MAJOR: CTA order of the raster kernels: 0 angle-major, 1 region-major (rows top to bottom), 2 region-major centre-out (measured: 2 wins)
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
@@ -88,7 +88,7 @@ struct Tuning {
     void load() {
         *this = Tuning();
         if (const char* e = getenv("CTDR_REGION_TILES")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) region_tiles = v; }
-        if (const char* e = getenv("CTDR_REGION_MAJOR")) region_major = atoi(e) != 0;
+        if (const char* e = getenv("CTDR_REGION_MAJOR")) { const int v = atoi(e); region_major = (v == 2) ? 2 : (v != 0); }
         if (const char* e = getenv("CTDR_DIRECT_MAX_BOX")) direct_max_box = atoi(e) < 0 ? -1 : atoi(e);
         no_batch_records = getenv("CTDR_NO_BATCH_RECORDS") != nullptr;
         if (const char* e = getenv("CTDR_GRAD_PER_VERTEX")) grad_per_vertex = atoi(e);
@@ -133,7 +133,7 @@ void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
     P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
     P.chunk_box = boxes;
-    P.region_major = tuning().region_major;     // 1 measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3)
+    P.region_major = tuning().region_major;     // region-major measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3); centre-out another -0.5 % / -1.3 %
     P.sr_rx = (P.regions_x + MAX_SR - 1) / MAX_SR;
     P.sr_ry = (P.regions_y + MAX_SR - 1) / MAX_SR;
     P.nsr_x = (P.regions_x + P.sr_rx - 1) / P.sr_rx;

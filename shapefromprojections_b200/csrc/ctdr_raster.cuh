@@ -204,6 +204,20 @@ k_super_lists(const short4* __restrict__ chunk_box, int NC, int H, int W, int ns
     if (tid == 0) scount[(long long)b * nsr + sr] = n;
 }
 
+// CTA order over the regions of an angle.  region_major == 2: centre-out — rows from the detector's middle row outwards,
+// and within a row the columns from the middle outwards — so a launch ends on the detector's border regions (few
+// faces, short CTAs) wherever the object sits: the tail of a small grid (an angle shard) is then made of light CTAs
+// (measured: -0.5 % on 720 angles of config 3, -1.3 % on a 90-angle shard and on the 1M-triangle mesh).
+__device__ __forceinline__ int centre_out(int k, int n) {
+    const int c = n >> 1;
+    return (k & 1) ? c - ((k + 1) >> 1) : c + (k >> 1);
+}
+__device__ __forceinline__ int region_of_rank(const RasterParams& P, int rank) {
+    if (P.region_major != 2) return rank;
+    const int ky = rank / P.regions_x, kx = rank - ky * P.regions_x;
+    return centre_out(ky, P.regions_y) * P.regions_x + centre_out(kx, P.regions_x);
+}
+
 // ------------------------------------------------------------------------------------------
 // shared memory
 // ------------------------------------------------------------------------------------------
@@ -1491,7 +1505,13 @@ __device__ __forceinline__ void prefetch_record(const RasterParams& P, int* L, i
     if (lane < 2) cp_async4(L + lane, r + lane);
 }
 
-// 8 resident CTAs (64 registers); 9 CTAs at 56 registers was measured slower (5.06 -> 6.19 ms on config 3)
+// 8 resident CTAs (64 registers); 9 CTAs at 56 registers was measured slower (5.06 -> 6.19 ms on config 3).  Also measured
+// and rejected: four single-warp CTAs per region (constant shared-memory addresses, no barrier, no tile counter:
+// 5.02 -> 5.08 ms); persistent warps pulling tile rows of any region from a device-wide queue (5.13 -> 5.67 ms: the four
+// warps of a CTA then work on four angles and thrash the 28 KB of L1); persistent CTAs taking (angle, region) items from
+// a device-wide queue with a rolling CTA-local tile ticket, so that no warp waits for the slowest warp of its CTA
+// (5.11 -> 5.79 ms, and 0.75 -> 0.82 ms on a 90-angle shard) — the hardware's CTA scheduler beats all three, although
+// regions of 4 x 4 instead of 8 x 8 tiles cost this kernel 14 % (per-CTA wind-down) and cheaper CTAs were the aim.
 template <bool STATS, bool GATHER>
 __global__ void __launch_bounds__(THREADS, 8)
 k_step_replay(const RasterParams P) {
@@ -1503,7 +1523,7 @@ k_step_replay(const RasterParams P) {
     asm volatile("mov.b32 %0, %0;" : "+r"(lane));            // pinned, see k_raster
     const int regions = P.regions_x * P.regions_y;
     const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
-    const int rr = P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions);
+    const int rr = region_of_rank(P, P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions));
     const int bflag = (int)P.bflag[(long long)b * regions + rr];
     if (bflag == 0) return;                                   // not recorded: k_raster<MODE_STEP> walks this region
     const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
@@ -1663,7 +1683,7 @@ k_raster(const RasterParams P) {
     // L2), or region-major (all angles of a region together: the last CTAs of the launch are then the
     // detector's bottom rows, usually empty — no heavy CTA is left running alone at the end of a small grid)
     const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
-    const int rr = P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions);
+    const int rr = region_of_rank(P, P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions));
     const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
     const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
     const short4* boxes = P.chunk_box + (long long)b * P.NC;

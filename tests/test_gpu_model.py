@@ -125,3 +125,68 @@ def test_cuda_graph_iteration_follows_the_eager_trajectory(cuda_lib, tmp_path):
     for k, tol in ((0, 2e-3), (5, 1e-2), (20, 5e-2)):
         assert abs(graphed[k] - eager[k + 3]) <= tol * eager[k + 3] + 1e-7, (k, graphed[k], eager[k + 3])
     assert graphed[-1] < eager[0] / 3
+
+
+def test_regularisers_at_config3_scale(cuda_lib):
+    """SURVEY row f3 at the mesh size of config 3 (V = 50 000, F = 100 000), on the device, values and gradients.
+    The reference builds a dense V x V Laplacian (softras_loss.py:31-52: 10 GB here) and scans every face for every edge
+    (:64-96: 1.5e10 comparisons); its definitions are restated with scipy.sparse / a per-edge dictionary instead."""
+    import time
+    import scipy.sparse as sp
+    from shapefromprojections_b200 import workloads
+    from shapefromprojections_b200.nn.softras_loss import FlattenLoss, LaplacianLoss
+    wl = workloads.make_workload("cfg3")
+    verts, faces = wl["verts"].astype(np.float64), wl["faces"].astype(np.int64)
+    V, F = verts.shape[0], faces.shape[0]
+    assert V == 50000 and F == 100000
+    rng = np.random.default_rng(0)
+    x = verts + 1e-3 * rng.normal(size=verts.shape)
+
+    # Laplacian, softras_loss.py:39-52: -1 on every (undirected) edge, degree on the diagonal, rows / (diag + 1e-10)
+    i = np.concatenate([faces[:, 0], faces[:, 1], faces[:, 1], faces[:, 2], faces[:, 2], faces[:, 0]])
+    j = np.concatenate([faces[:, 1], faces[:, 0], faces[:, 2], faces[:, 1], faces[:, 0], faces[:, 2]])
+    A = sp.coo_matrix((np.ones(i.size), (i, j)), shape=(V, V)).tocsr()
+    A.data[:] = 1.0                                             # assignment, not accumulation (:41-46)
+    deg = np.asarray(A.sum(1)).ravel()
+    L = sp.diags(deg / (deg + 1e-10)) - sp.diags(1.0 / (deg + 1e-10)) @ A
+    lap_ref = np.square(L @ x).sum(1)
+    glap_ref = 2.0 * (L.T @ (L @ x))                            # d sum(lap) / dx
+
+    t0 = time.time()
+    lap = LaplacianLoss(torch.as_tensor(verts), torch.as_tensor(faces)).cuda()
+    flat = FlattenLoss(torch.as_tensor(faces)).cuda()
+    build_s = time.time() - t0
+    xt = torch.as_tensor(x, dtype=torch.float32, device="cuda").requires_grad_(True)
+    out = lap(xt)
+    out.sum().backward()
+    torch.cuda.synchronize()
+    assert np.abs(out.detach().cpu().numpy() - lap_ref).max() <= 1e-5 * lap_ref.max() + 1e-9
+    g = xt.grad.cpu().numpy()
+    assert np.linalg.norm(g - glap_ref) <= 1e-4 * np.linalg.norm(glap_ref)
+
+    # flatten loss, softras_loss.py:64-136: edges = the (v0,v1) and (v1,v2) sides, wings from the first two faces (in
+    # face order) that contain the edge
+    firsttwo = {}
+    for fi, (a, b, c) in enumerate(faces):
+        for u, v, w in ((a, b, c), (b, c, a), (c, a, b)):
+            firsttwo.setdefault((min(u, v), max(u, v)), []).append(w)
+    edges = sorted(set(tuple(sorted(e)) for e in np.concatenate([faces[:, 0:2], faces[:, 1:3]])))
+    v0 = np.array([e[0] for e in edges]); v1 = np.array([e[1] for e in edges])
+    v2 = np.array([firsttwo[e][0] for e in edges]); v3 = np.array([firsttwo[e][1] for e in edges])
+    c10, c20, c30 = x[v1] - x[v0], x[v2] - x[v0], x[v3] - x[v0]
+    n0, n1 = np.cross(c10, c20), -np.cross(c10, c30)
+    flat_ref = (1.0 - (n0 * n1).sum(1) / (np.linalg.norm(n0, axis=1) * np.linalg.norm(n1, axis=1))).mean()
+    xt.grad = None
+    fl = flat(xt)
+    fl.backward()
+    torch.cuda.synchronize()
+    assert abs(float(fl) - flat_ref) <= 1e-5 * abs(flat_ref) + 1e-7, (float(fl), flat_ref)
+    assert torch.isfinite(xt.grad).all() and float(xt.grad.abs().sum()) > 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        xt.grad = None
+        (lap(xt).mean() + flat(xt)).backward()
+    e1.record(); torch.cuda.synchronize()
+    print(f"regularisers at V={V}, F={F}: tables built in {build_s:.2f} s on the host; Laplacian + flatten forward + backward "
+          f"{e0.elapsed_time(e1) / 20:.3f} ms per iteration on the device")
