@@ -161,6 +161,15 @@ int launch_chunk_bbox(const RasterParams& P, short4* boxes, short4* face_boxes, 
 
 template <int MODE, bool DIRECT, bool LINKED, bool GATHER>
 void launch_raster_variant(const RasterParams& P, unsigned blocks, size_t smem, cudaStream_t st) {
+    if constexpr (MODE == MODE_FWD && GATHER) {
+        // the fused projector's forward without a count output: no count tile in shared memory, so eight CTAs fit
+        // beside 60 KB of L1 instead of 28 KB
+        if (!P.cnt) {
+            if (P.stats) k_raster<MODE, false, DIRECT, true, LINKED, GATHER, true><<<blocks, THREADS, smem, st>>>(P);
+            else k_raster<MODE, false, DIRECT, false, LINKED, GATHER, true><<<blocks, THREADS, smem, st>>>(P);
+            return;
+        }
+    }
     if (P.stats) k_raster<MODE, false, DIRECT, true, LINKED, GATHER><<<blocks, THREADS, smem, st>>>(P);
     else k_raster<MODE, false, DIRECT, false, LINKED, GATHER><<<blocks, THREADS, smem, st>>>(P);
 }
@@ -197,6 +206,9 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool l
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else if (linked && MODE == MODE_STEP) {
         // replay-only residual/backward kernel over the batches the forward sweep recorded
+        if (const char* e = getenv("CTDR_PROBE_CARVEOUT")) {       // probe: shared-memory carve-out in percent (L1 = the rest)
+            cudaFuncSetAttribute(k_step_replay<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        }
         if (P.vt) {
             if (P.stats) k_step_replay<true, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
             else k_step_replay<false, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
@@ -486,6 +498,7 @@ struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
     float4* gvt;         // [window, V] per-vertex cotangents of the raster backward (default backward)
     float4* vt;          // [window, V] per-vertex transform records
+    AngleConst* atab;    // [window] per-angle constants of the vertex stage
     float* fs;           // [window, F] per-face attenuation terms (deterministic backward)
     double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
     // batch records of the residual step (forward sweep records, residual/backward sweep replays)
@@ -516,11 +529,11 @@ size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0, boo
     const int NC = (F + CHUNK - 1) / CHUNK;
     const size_t per_face = (face_arrays ? 40 + (bwd ? 36 + 4 : 0) : 0) + sizeof(short4);
     return (bwd && H > 0 ? batch_record_bytes_per_angle(F, H, W) : 0) + (size_t)V * sizeof(float4) * (bwd ? 2 : 1) + (size_t)F * per_face + (size_t)NC * (sizeof(short4) + MAX_SR * MAX_SR * sizeof(int)) +
-           MAX_SR * MAX_SR * sizeof(int) + 512;
+           MAX_SR * MAX_SR * sizeof(int) + sizeof(AngleConst) + 512;
 }
 
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws, bool face_arrays = true) {
-    const size_t slack = 28 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    const size_t slack = 30 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
     const size_t per = project_per_angle_bytes(V, F, bwd, H, W, face_arrays);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -532,6 +545,7 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     char* p = static_cast<char*>(base);
     size_t off = 0;
     ws->vt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
+    ws->atab = reinterpret_cast<AngleConst*>(p + off); off += align_up((size_t)win * sizeof(AngleConst), 256);
     ws->p6 = ws->len3 = ws->ff = nullptr;
     if (face_arrays) {
         ws->p6 = reinterpret_cast<float*>(p + off);   off += align_up((size_t)win * F * 24, 256);
@@ -568,6 +582,15 @@ int launch_vertex_forward(const VertexParams& P, float* p6, float* len3, float* 
     if (blocks > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*F too large for one launch");
     k_vertex_forward<<<(unsigned)blocks, 256, 0, st>>>(P, p6, len3, ff);
     CTDR_LAUNCHED(1, "k_vertex_forward launch");
+    return 0;
+}
+
+// per-angle constants of one angle window, formed once; the window's vertex-stage kernels then read the table
+int launch_angle_table(VertexParams& P, AngleConst* tab, cudaStream_t st) {
+    P.atab = nullptr;
+    k_angle_table<<<(unsigned)((P.B + 127) / 128), 128, 0, st>>>(P, tab);
+    CTDR_LAUNCHED(1, "k_angle_table launch");
+    P.atab = tab;
     return 0;
 }
 
@@ -885,7 +908,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 28 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    return per * (size_t)win + 30 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -904,7 +927,8 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
@@ -936,7 +960,8 @@ int ctdr_project_forward_multi(int geom_kind, const float* geom, int nangles, co
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus_kxn, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         P.im = im_kxbxhxw + (size_t)b0 * hw; P.n_out = n_out; P.out_stride = (long long)B * (long long)hw;
@@ -967,7 +992,8 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
     const size_t hw = (size_t)H * W;
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
@@ -1049,7 +1075,8 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
     CTDR_MARK(tm, -1, stream);
     for (int b0 = 0; b0 < B; b0 += ws.window) {
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
-        const VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
+        if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);

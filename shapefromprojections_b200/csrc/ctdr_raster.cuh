@@ -223,7 +223,11 @@ __device__ __forceinline__ int region_of_rank(const RasterParams& P, int rank) {
 // ------------------------------------------------------------------------------------------
 constexpr int SLOT_VEC = 5;       // float4 per staged face slot (stride 80 B: conflict-free LDS.128)
 
-struct __align__(16) WarpSmem {
+// CNT = false: no fragment-count tile (the fused projector's forward never asks for counts) — with it the CTA fits
+// eight times beside 60 KB of L1 instead of 28 KB (see k_raster)
+template <bool CNT>
+struct __align__(16) WarpSmemT {
+    static constexpr bool HAS_CNT = CNT;
     // Staged chunk, array of structures, nonempty faces compacted to the low slots:
     //   v0 = (ax, ay, m, p)   v1 = (n, q, k3, box)   v2 = (d, 1/d) as two doubles
     //   v3 = (r0, r1, r2, cA) v4 = (cB, excl, labels/sign word, face id)
@@ -232,23 +236,30 @@ struct __align__(16) WarpSmem {
     // labels/sign word (MODE_MULTI): label_in | label_out << 12 | (sign < 0) << 24.
     float4 slot[32 * SLOT_VEC];
     // Per-row pixel spans of the staged faces inside the tile: one byte per (slot, row) =
-    // first column << 4 | last column (tile-relative); first > last marks an empty row.
-    unsigned char span[32][TILE];
+    // first column << 4 | last column (tile-relative); first > last marks an empty row.  Once the batch's candidates
+    // are walked the same bytes hold the list of pixels hit by more than one face of the batch (cpix).
+    union {
+        unsigned char span[32][TILE];
+        unsigned char cpix[TILE_PIX];
+    };
     union {
         float mom[3][32];        // backward: sum g, sum g*k1, sum g*k2 per slot
         struct {
             unsigned hitm[TILE_PIX];         // forward: which slots of the current batch hit each pixel
-            unsigned char cpix[TILE_PIX];    // forward: pixels hit by more than one face of the batch
         } f;
     };
+    // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel.  The backward modes of k_raster use its
+    // first 256 bytes as the tail of the prefix-sum overlay (prefix_e0) and the next 144 as the record landing zone.
+    int   cntv[CNT ? TILE_PIX : 4];
     // queue of faces whose box overlaps the tile, in face order (drained 32 at a time)
     int    qface[64];
-    // tile accumulators
-    float acc[TILE_PIX];         // forward: running sinogram; backward: g (0 where no gradient)
-    int   cntv[TILE_PIX];        // forward: fragment count; MODE_FRAG: CSR cursor, -1 = invalid pixel
+    // tile accumulator
+    float acc[TILE_PIX];                     // forward: running sinogram; backward: g (0 where no gradient)
 };
+typedef WarpSmemT<true> WarpSmem;
 
-struct CtaSmem {
+template <bool CNT>
+struct CtaSmemT {
     // chunks overlapping the region, ascending: chunk id (20 bits) | first/last tile column and first/last
     // tile row of its box inside the region (3 bits each), so a tile tests a chunk without touching memory
     int    list_id[LIST_CAP];
@@ -256,9 +267,10 @@ struct CtaSmem {
     int    list_n;
     int    next_tile;
     int    rec_fail;              // batch recording ran out of record space somewhere in this region
-    WarpSmem warp[WARPS];
+    WarpSmemT<CNT> warp[WARPS];
     // the dynamic shared memory holds float gmus[n_mus] (backward modes) or the MODE_MULTI extras
 };
+typedef CtaSmemT<true> CtaSmem;
 
 __device__ __forceinline__ bool box_overlap(const short4 bx, int x0, int y0, int x1, int y1) {
     return (bx.x <= x1) & (bx.z >= x0) & (bx.y <= y1) & (bx.w >= y0);
@@ -355,8 +367,8 @@ struct ThreadStatsT {
 // ------------------------------------------------------------------------------------------
 // one (tile, chunk): stage the chunk's faces, spread candidates over lanes, evaluate coverage
 // ------------------------------------------------------------------------------------------
-template <int MODE, bool EXACT_DIV, class ThreadStats>
-__device__ __forceinline__ void process_batch(const RasterParams& P, WarpSmem& S, float* gmus,
+template <int MODE, bool EXACT_DIV, class ThreadStats, class WS>
+__device__ __forceinline__ void process_batch(const RasterParams& P, WS& S, float* gmus,
                                               int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                               int lane, ThreadStats& st) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
@@ -610,12 +622,12 @@ __device__ __forceinline__ bool cover_slot(const float4 v0, const float4 v1, con
 
 // Pixels hit by several faces of the current batch: recompute them over exactly the faces in their
 // hit mask, in ascending face order (kept out of line: rare, and it keeps the hot loop's code small).
-template <bool EXACT_DIV>
-__device__ __noinline__ void redo_conflicted(WarpSmem& S, int ncp, int tx0, int ty0, int lane) {
+template <bool EXACT_DIV, class WS>
+__device__ __noinline__ void redo_conflicted(WS& S, int ncp, int tx0, int ty0, int lane) {
 #pragma unroll 1
     for (int base = 0; base < ncp; base += 32) {
         const bool have = base + lane < ncp;
-        const int pix = have ? (int)S.f.cpix[base + lane] : 0;
+        const int pix = have ? (int)S.cpix[base + lane] : 0;
         const int px = pix & 15, py = pix >> 4;
         float acc = S.acc[pix];
         unsigned fm = have ? S.f.hitm[pix] : 0u;
@@ -648,8 +660,10 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // Replay of recorded batches (residual/backward sweep): the next record is fetched into a landing zone in
 // the part of the forward/backward union the backward does not use (behind the three moment rows), while
 // the current batch is being processed.
-__device__ __forceinline__ int* record_landing(WarpSmem& S) { return S.cntv; }   // the count tile is unused by the backward modes
-__device__ __forceinline__ void prefetch_record(const RasterParams& P, WarpSmem& S, int off, int lane) {
+template <class WS>
+__device__ __forceinline__ int* record_landing(WS& S) { return S.cntv + 64; }   // the count tile is unused by the backward modes (its first 256 B: prefix overlay)
+template <bool CNT>
+__device__ __forceinline__ void prefetch_record(const RasterParams& P, WarpSmemT<CNT>& S, int off, int lane) {
     const int* r = P.brec + (long long)off * BREC_INTS;
     int* L = record_landing(S);
     cp_async4(L + 2 + lane, r + 2 + lane);
@@ -665,7 +679,8 @@ __device__ __forceinline__ float* multi_xacc(float* dyn, int warp) {
 
 // MODE_MULTI: accumulator of output k for this warp's tile (k = 0: acc, k = 1: the count array's
 // storage, k >= 2: extra dynamic shared memory)
-__device__ __forceinline__ float* multi_acc(WarpSmem& S, float* xacc, int k) {
+template <class WS>
+__device__ __forceinline__ float* multi_acc(WS& S, float* xacc, int k) {
     return k == 0 ? S.acc : (k == 1 ? reinterpret_cast<float*>(S.cntv) : xacc + (k - 2) * TILE_PIX);
 }
 
@@ -673,14 +688,14 @@ __device__ __forceinline__ float* multi_acc(WarpSmem& S, float* xacc, int k) {
 // sinograms share the coverage test and the interpolated length and differ only in the
 // attenuation coefficients, so each of them receives exactly the update sequence of a
 // single-output pass with its own mus (diff_fp_for.cu:174-190).  Returns the non-positive-length count.
-template <bool EXACT_DIV>
-__device__ __noinline__ unsigned redo_multi(WarpSmem& S, float* xacc, const float* __restrict__ mus, int n_mus,
+template <bool EXACT_DIV, class WS>
+__device__ __noinline__ unsigned redo_multi(WS& S, float* xacc, const float* __restrict__ mus, int n_mus,
                                             int n_out, int ncp, int tx0, int ty0, int lane) {
     unsigned nonpos = 0u;
 #pragma unroll 1
     for (int base = 0; base < ncp; base += 32) {
         const bool have = base + lane < ncp;
-        const int pix = have ? (int)S.f.cpix[base + lane] : 0;
+        const int pix = have ? (int)S.cpix[base + lane] : 0;
         const int px = pix & 15, py = pix >> 4;
         float a[MAX_OUT];
 #pragma unroll
@@ -767,8 +782,8 @@ __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo,
     return xs <= xe;
 }
 
-template <int MODE, bool EXACT_DIV, bool DIRECT, bool GATHER, class ThreadStats>
-__device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WarpSmem& S, float* gmus,
+template <int MODE, bool EXACT_DIV, bool DIRECT, bool GATHER, class ThreadStats, class WS>
+__device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
                                                       int lane, ThreadStats& st) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
@@ -1054,7 +1069,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
     if (!IS_FWD && !IS_MULTI && mine) { fm0 = S.mom[0][rank]; fa1 = S.mom[1][rank]; fa2 = S.mom[2][rank]; }
     }   // general path
 
-    if (IS_MULTI) {
+    if constexpr (IS_MULTI) {
         // ---- every pixel hit by the batch is (re)computed pixel-parallel for all outputs -----------
         const uint4 h0 = *reinterpret_cast<const uint4*>(S.f.hitm + 4 * lane);
         const uint4 h1 = *reinterpret_cast<const uint4*>(S.f.hitm + 128 + 4 * lane);
@@ -1064,11 +1079,11 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         for (int k = 0; k < 8; ++k) {
             const bool hit = hm[k] != 0u;
             const unsigned m = __ballot_sync(FULL, hit);
-            if (hit) S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)((k < 4 ? 0 : 128) + 4 * lane + (k & 3));
+            if (hit) S.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)((k < 4 ? 0 : 128) + 4 * lane + (k & 3));
             ncp += __popc(m);
         }
         __syncwarp();
-        if (ncp) st.nonpos += redo_multi<EXACT_DIV>(S, multi_xacc(gmus, threadIdx.x >> 5), P.mus, P.n_mus,
+        if (ncp) st.nonpos += redo_multi<EXACT_DIV, WS>(S, multi_xacc(gmus, threadIdx.x >> 5), P.mus, P.n_mus,
                                                     P.n_out, ncp, tx0, ty0, lane);
         __syncwarp();
         return;
@@ -1085,7 +1100,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
         const float ov[8] = {old0.x, old0.y, old0.z, old0.w, old1.x, old1.y, old1.z, old1.w};
         unsigned mymask[8];
         bool anymulti = false;
-        if (P.cnt) {                                                  // coverage counts are optional
+        if (WS::HAS_CNT && P.cnt) {                                   // coverage counts are optional
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (hm[k]) S.cntv[(k < 4 ? 0 : 128) + 4 * lane + (k & 3)] += __popc(hm[k]);   // :192
@@ -1105,7 +1120,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
                 if (m) {
                     if (multi) {
                         S.acc[pix] = ov[k];
-                        S.f.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)pix;
+                        S.cpix[ncp + __popc(m & lanemask_lt())] = (unsigned char)pix;
                     }
                     ncp += __popc(m);
                 }
@@ -1117,7 +1132,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, War
             for (int k = 0; k < 8; ++k)
                 if (mymask[k]) S.f.hitm[(k < 4 ? 0 : 128) + 4 * lane + (k & 3)] = mymask[k];
             __syncwarp();
-            redo_conflicted<EXACT_DIV>(S, ncp, tx0, ty0, lane);
+            redo_conflicted<EXACT_DIV, WS>(S, ncp, tx0, ty0, lane);
         }
         __syncwarp();
         return;
@@ -1164,10 +1179,11 @@ __device__ unsigned long long g_rowstats[4];
 constexpr int PREFIX_STRIDE = TILE + 1;
 // The prefix sums are kept in float64: a span sum is a DIFFERENCE of two prefixes, and with fp32 prefixes its
 // error would be an ulp of the whole row's running sum (measured: 2e-4 relative on grad_p6, the moments then
-// cancel against each other) instead of an ulp of the span sum.  2 x 16 x 17 doubles = 4352 B: exactly the
-// forward-only part of WarpSmem (slot + span + hit masks), which the backward modes do not use.
-__device__ __forceinline__ double* prefix_e0(WarpSmem& S) { return reinterpret_cast<double*>(S.slot); }
-static_assert(offsetof(WarpSmem, qface) >= 2 * TILE * PREFIX_STRIDE * sizeof(double), "prefix arrays overlay slot + span + hit masks");
+// cancel against each other) instead of an ulp of the span sum.  2 x 16 x 17 doubles = 4352 B: the forward-only
+// part of WarpSmem (slot + span + hit masks = 4096 B) and the head of the count tile, which the backward modes do not use.
+template <bool CNT>
+__device__ __forceinline__ double* prefix_e0(WarpSmemT<CNT>& S) { return reinterpret_cast<double*>(S.slot); }
+static_assert(offsetof(WarpSmem, cntv) + 64 * sizeof(int) >= 2 * TILE * PREFIX_STRIDE * sizeof(double), "prefix arrays overlay slot + span + hit masks + the head of the count tile");
 
 // per-warp shared memory of the replay-only residual/backward kernel (k_step_replay): nothing of the forward's state
 struct __align__(16) ReplayWarpSmem {
@@ -1664,14 +1680,16 @@ k_step_replay(const RasterParams P) {
 // batches of every tile; MODE_STEP + LINKED is a replay-only kernel (no region lists, no queues) that skips
 // the regions the forward sweep could not record — those are done by the ordinary MODE_STEP kernel, launched
 // right after it with bmode == 2, which in turn skips the recorded ones.
-template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false, bool GATHER = false>
+template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false, bool GATHER = false, bool NOCNT = false>
 __global__ void __launch_bounds__(THREADS, 8)
 k_raster(const RasterParams P) {
     constexpr bool RECORD = LINKED && MODE == MODE_FWD;
     constexpr bool REPLAY = LINKED && MODE == MODE_STEP;
     // fixed-size state in STATIC shared memory (addresses are link-time constants: no base pointer to keep
     // or rebuild in the hot loops); the dynamic part holds grad_mus accumulators / MODE_MULTI extras
-    __shared__ CtaSmem C;
+    static_assert(!NOCNT || MODE == MODE_FWD, "only the forward sweep runs without the count tile");
+    typedef WarpSmemT<!NOCNT> WS;
+    __shared__ CtaSmemT<!NOCNT> C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* gmus = reinterpret_cast<float*>(smem_raw);
 
@@ -1695,7 +1713,7 @@ k_raster(const RasterParams P) {
     // otherwise rebuilds it from %tid / %cluster_ctarank (two S2R + four ALU instructions) at dozens of places in the hot loops
     unsigned sbase = (unsigned)__cvta_generic_to_shared(&C.warp[warp]);
     asm volatile("mov.b32 %0, %0;" : "+r"(sbase));
-    WarpSmem& S = *reinterpret_cast<WarpSmem*>(__cvta_shared_to_generic(sbase));
+    WS& S = *reinterpret_cast<WS*>(__cvta_shared_to_generic(sbase));
     ThreadStatsT<STATS> st;
 
     constexpr bool K_BWD = (MODE == MODE_BWD || MODE == MODE_STEP);
@@ -1843,10 +1861,10 @@ k_raster(const RasterParams P) {
                 for (int k = 0; k < TILE_PIX / 32; ++k) S.f.hitm[lane + 32 * k] = 0u;
                 if (first) {
 #pragma unroll
-                    for (int k = 0; k < TILE_PIX / 32; ++k) { S.acc[lane + 32 * k] = 0.0f; S.cntv[lane + 32 * k] = 0; }
+                    for (int k = 0; k < TILE_PIX / 32; ++k) { S.acc[lane + 32 * k] = 0.0f; if (WS::HAS_CNT) S.cntv[lane + 32 * k] = 0; }
                 } else {
                     tile_load<float>(S.acc, P.im, 0.0f, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
-                    if (P.cnt) tile_load<int>(S.cntv, P.cnt, 0, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+                    if (WS::HAS_CNT && P.cnt) tile_load<int>(S.cntv, P.cnt, 0, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
                 }
             } else if (MODE == MODE_MULTI) {
 #pragma unroll
@@ -2018,7 +2036,7 @@ k_raster(const RasterParams P) {
             if (MODE == MODE_FWD) {
                 if (recording && !last && lane == 0) P.btail[CTDR_HEAD_INDEX] = roff;
                 tile_store<float>(P.im, S.acc, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
-                if (P.cnt) tile_store<int>(P.cnt, S.cntv, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
+                if (WS::HAS_CNT && P.cnt) tile_store<int>(P.cnt, S.cntv, b, P.H, P.W, tx0, ty0, tx1, ty1, lane);
             } else if (MODE == MODE_MULTI) {
                 for (int o = 0; o < P.n_out; ++o)
                     tile_store<float>(P.im + (long long)o * P.out_stride, multi_acc(S, xacc, o), b, P.H, P.W, tx0, ty0, tx1, ty1, lane);

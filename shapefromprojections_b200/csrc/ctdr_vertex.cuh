@@ -21,17 +21,30 @@ struct VertexParams {
     const int* faces;             // [F,3]
     float msv;                    // max_sino_val as float32
     float P00, P11, P13;          // orthographic matrix entries (projection.py:16-30), PARALLEL3D only
+    const struct AngleConst* atab;  // [B] per-angle constants formed once by k_angle_table, or null (computed per thread)
 };
 
-struct AngleConst {
+struct __align__(16) AngleConst {
     // PARALLEL3D
     float ct, st;
     // *_VEC
     float Sx, Sy, Sz, N0, N1, ux, uy, vz, DSx, DSy, DSz, coeff;
-    bool use_x;
+    int use_x;
+    int pad_;
 };
+static_assert(sizeof(AngleConst) == 64, "one angle = four 16-byte loads from the angle table");
 
 __device__ __forceinline__ AngleConst angle_const(const VertexParams& P, int b) {
+    if (P.atab) {
+        // fused projector: the angle's constants were formed once (k_angle_table, same arithmetic) instead of by every
+        // thread of the three vertex-stage kernels
+        const float4* t = reinterpret_cast<const float4*>(P.atab + b);
+        const float4 a = __ldg(t), c = __ldg(t + 1), d = __ldg(t + 2), e = __ldg(t + 3);
+        AngleConst A;
+        A.ct = a.x; A.st = a.y; A.Sx = a.z; A.Sy = a.w; A.Sz = c.x; A.N0 = c.y; A.N1 = c.z; A.ux = c.w;
+        A.uy = d.x; A.vz = d.y; A.DSx = d.z; A.DSy = d.w; A.DSz = e.x; A.coeff = e.y; A.use_x = __float_as_int(e.z); A.pad_ = 0;
+        return A;
+    }
     AngleConst A = {};
     const long long row = P.idx_angles[b];
     if ((unsigned long long)row >= (unsigned long long)P.nangles) {
@@ -70,7 +83,7 @@ __device__ __forceinline__ AngleConst angle_const(const VertexParams& P, int b) 
     A.DSx = __fsub_rn(__fsub_rn(px, __fmul_rn(hh, vx)), __fmul_rn(hw, A.ux));
     A.DSy = __fsub_rn(__fsub_rn(py, __fmul_rn(hh, vy)), __fmul_rn(hw, A.uy));
     A.DSz = __fsub_rn(__fsub_rn(pz, __fmul_rn(hh, A.vz)), __fmul_rn(hw, uz));
-    A.use_x = fabsf(A.ux) > fabsf(A.uy);                                // :168
+    A.use_x = fabsf(A.ux) > fabsf(A.uy) ? 1 : 0;                        // :168
     return A;
 }
 
@@ -119,6 +132,14 @@ __device__ __forceinline__ VertexOut project_vertex(const VertexParams& P, const
     o.px = A.use_x ? __fdiv_rn(dx, A.ux) : __fdiv_rn(dy, A.uy);                  // :171-172
     o.py = __fdiv_rn(dz, A.vz);                                                  // :173
     return o;
+}
+
+// one thread per window angle: the per-angle constants of the vertex stage, once (VertexParams::atab must be null here)
+__global__ void __launch_bounds__(128)
+k_angle_table(const VertexParams P, AngleConst* __restrict__ tab) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    tab[b] = angle_const(P, b);
 }
 
 // thread per (angle, face): p6 / len3 / ff exactly as handed to Rasterizer.apply
