@@ -503,6 +503,7 @@ struct ProjectWs {
     double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
     // batch records of the residual step (forward sweep records, residual/backward sweep replays)
     int* brec; int* bhead; int* btail; unsigned char* bflag; int* bcursor; int bcap;
+    int4* xlist;         // faces the forward sweep could not record as spans (RasterParams::xlist); its counter is bcursor[-1]
     RasterWs rws;
     int window;   // angles per window
 };
@@ -533,7 +534,7 @@ size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0, boo
 }
 
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws, bool face_arrays = true) {
-    const size_t slack = 30 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    const size_t slack = 32 * 256 + XLIST_CAP * sizeof(int4) + 2 * DET_LOSS_BLOCKS * sizeof(double);
     const size_t per = project_per_angle_bytes(V, F, bwd, H, W, face_arrays);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -570,7 +571,9 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
         ws->bhead = reinterpret_cast<int*>(p + off);   off += align_up((size_t)win * tiles * sizeof(int), 256);
         ws->btail = reinterpret_cast<int*>(p + off);   off += align_up((size_t)win * tiles * sizeof(int), 256);
         ws->bflag = reinterpret_cast<unsigned char*>(p + off); off += align_up((size_t)win * regions2, 256);
-        ws->bcursor = reinterpret_cast<int*>(p + off); off += align_up((size_t)win * sizeof(int), 256);
+        // [0]: entries of xlist, [1 .. win]: record cursors — one memset zeroes both
+        ws->bcursor = reinterpret_cast<int*>(p + off) + 1; off += align_up(((size_t)win + 1) * sizeof(int), 256);
+        ws->xlist = reinterpret_cast<int4*>(p + off); off += align_up((size_t)XLIST_CAP * sizeof(int4), 256);
     }
     raster_ws_layout((int)win, F, H, W, false, false, &ws->rws, p + off);
     return 0;
@@ -908,7 +911,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 30 * 256 + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    return per * (size_t)win + 32 * 256 + XLIST_CAP * sizeof(int4) + 2 * DET_LOSS_BLOCKS * sizeof(double);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -1086,8 +1089,9 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         P.im = phat + (size_t)b0 * hw;
         if (!det) {             // the forward sweep records its face batches for the residual/backward sweep
             P.bmode = 1; P.brec = ws.brec; P.bhead = ws.bhead; P.btail = ws.btail; P.bflag = ws.bflag; P.bcursor = ws.bcursor; P.bcap = ws.bcap;
+            P.xlist = ws.xlist; P.xcount = ws.bcursor - 1;
             if (tuning().no_batch_records || (flags & CTDR_FLAG_NO_PREFILTER)) P.bmode = 0;   // tuning/debug: no linking
-            if (P.bmode) CTDR_CUDA(cudaMemsetAsync(ws.bcursor, 0, (size_t)nb * sizeof(int), stream), "memset record cursors");
+            if (P.bmode) CTDR_CUDA(cudaMemsetAsync(ws.bcursor - 1, 0, ((size_t)nb + 1) * sizeof(int), stream), "memset record cursors");
         }
         const bool linked = P.bmode == 1;
         CTDR_MARK(tm, CTDR_STAGE_MEMSET, stream);
@@ -1116,7 +1120,13 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
             continue;
         }
         // linked sweeps: the replay-only kernel takes the recorded regions, the ordinary one the rest
-        if (linked) { if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc; }
+        if (linked) {
+            if (int rc = launch_raster<MODE_STEP>(P, flags, stream, true)) return rc;
+            // the few faces whose coverage could not be recorded as row intervals
+            if (P.vt) k_step_facelist<true><<<XLIST_CAP / 128, 128, 0, stream>>>(P);
+            else k_step_facelist<false><<<XLIST_CAP / 128, 128, 0, stream>>>(P);
+            CTDR_LAUNCHED(1, "k_step_facelist launch");
+        }
         if (int rc = launch_raster<MODE_STEP>(P, flags, stream)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_RASTER_STEP, stream);
         if (pervertex) { if (int rc = launch_vertex_backward_pervertex(VP, ws.gvt, grad_verts, stream)) return rc; }

@@ -30,9 +30,22 @@
 
 namespace ctdr {
 
+#ifdef CTDR_PROBE_ROWSTATS
+__device__ unsigned long long g_rowstats[4];     // diagnostic build only (tools/probe_rowstats.py)
+#endif
 enum RasterMode { MODE_FWD = 0, MODE_FRAG = 1, MODE_BWD = 2, MODE_STEP = 3, MODE_MULTI = 4 };
 constexpr int MAX_OUT = 4;       // sinograms per MODE_MULTI pass
-constexpr int BREC_INTS = 34;    // ints per batch record
+// Batch record of the linked sweeps: what the forward sweep found for one batch of <= 32 faces of one tile,
+//   [0] next record of the tile or -1, [1] face count | flags << 8, [2 .. 33] face id | (facing < 0) << 31,
+//   [36 .. 43] one byte per face: first row of the face in the tile | (rows - 1) << 4,
+//   [44 .. 171] 16 bytes per face: the pixels of each TILE row the face covers, first column << 4 | last column
+//               (0x10 = none) — the exact coverage decided by the forward's own test, so the residual/backward sweep
+//               needs no edge functions, margins or exact re-tests: its fragments are the forward's by construction.
+constexpr int BREC_INTS = 172;   // ints per batch record (688 B, a multiple of 16)
+constexpr int BREC_INFO = 36, BREC_SPANS = 44;
+constexpr int BREC_FLAG_EMPTY = 0x100;   // no face of the batch covers a pixel of the tile: nothing to replay
+constexpr int XLIST_CAP = 8192;          // (angle, face, tile) triples per angle window whose coverage is not one interval per row
+constexpr unsigned SPAN_NONE4 = 0x10101010u;
 
 struct RasterParams {
     // inputs at the Rasterizer boundary (rasterizer.py:13)
@@ -97,6 +110,11 @@ struct RasterParams {
     int*   btail;           // [B, tiles]: last record so far (only regions whose list takes several segments)
     unsigned char* bflag;   // [B, regions]: 0 = not recorded (fall back to the walk), 1 = recorded, 2 = empty region
     int*   bcursor;         // [B] next free record of each angle's slice
+    // Faces whose coverage on some row of a tile is not one interval (faces without a usable area whose pixel centres
+    // fall erratically on their line: a few per million batches) cannot be recorded as spans: the forward sweep lists
+    // them here and leaves their rows empty in the record; k_step_facelist handles them pixel by pixel.
+    int4*  xlist;           // [XLIST_CAP] {angle, face, tile x0, tile y0}
+    int*   xcount;          // entries appended (may exceed XLIST_CAP: the region is then left to the walking kernel)
     int    bcap;            // records per angle
     int region_major;       // CTA order, see k_raster
     int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
@@ -255,6 +273,9 @@ struct __align__(16) WarpSmemT {
     int    qface[64];
     // tile accumulator
     float acc[TILE_PIX];                     // forward: running sinogram; backward: g (0 where no gradient)
+    // recording forward sweep: per face (queue lane) the tile rows whose coverage must be re-derived from the hit masks
+    // (a candidate inside the conservative span failed, or its lane had no room left to remember it); 16 bits per face
+    unsigned susp[16];
 };
 typedef WarpSmemT<true> WarpSmem;
 
@@ -653,6 +674,10 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -782,10 +807,12 @@ __device__ __forceinline__ bool row_span(const SpanSetup& sp, float t, int x_lo,
     return xs <= xe;
 }
 
-template <int MODE, bool EXACT_DIV, bool DIRECT, bool GATHER, class ThreadStats, class WS>
+// RECSPAN (recording forward sweep): `rec` = this batch's record (negative: none) receives the exact coverage; a face
+// whose coverage on some row is not one interval goes to RasterParams::xlist instead (its rows stay empty in the record)
+template <int MODE, bool EXACT_DIV, bool DIRECT, bool GATHER, bool RECSPAN, class ThreadStats, class WS>
 __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS& S, float* gmus,
                                                       int b, int nb, int tx0, int ty0, int tx1, int ty1,
-                                                      int lane, ThreadStats& st) {
+                                                      int lane, ThreadStats& st, int rec, int* rec_fail) {
     constexpr bool IS_FWD = (MODE == MODE_FWD);
     constexpr bool IS_MULTI = (MODE == MODE_MULTI);          // gmus doubles as the extra accumulators
     const bool queued = lane < nb;
@@ -807,6 +834,15 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
     }
     __syncwarp();                                       // queue entries consumed
     const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+    if (RECSPAN) {
+        *reinterpret_cast<uint4*>(S.span[lane]) = make_uint4(SPAN_NONE4, SPAN_NONE4, SPAN_NONE4, SPAN_NONE4);
+        if (lane < 16) S.susp[lane] = 0u;
+    }
+    bool irregular = false;
+    // recording: the (at most two) candidates this lane saw fail the exact test at an END of their row's conservative
+    // span, 16 bits each: 1 | queue lane << 1 | tile row << 6 | (right end) << 10; applied to the span bytes after the walk
+    // (other lanes still read the spans during it)
+    unsigned myfail = 0u;
 
     if (lane == 0) st.visits++;
     if (fneg) sgn = -1.0f;                                            // diff_fp_for.cu:94-96
@@ -849,6 +885,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
             __syncwarp();
         }
         int r = -1, x = 0, xe = -1;
+        int cfirst = TILE, clast = -1, ccount = 0;                    // RECSPAN: covered columns of the current row
         bool active = queued;
 #pragma unroll 1
         while (active) {                                              // first non-empty row
@@ -862,6 +899,7 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
                 float k1, k2, w0, w1, w2;
                 const bool in = cover_slot<EXACT_DIV>(v0, v1, dy, (float)x, (float)(cy0 + r), k1, k2, w0, w1, w2);
                 st.cand++;
+                if (RECSPAN && in) { cfirst = min(cfirst, x - tx0); clast = x - tx0; ++ccount; }
                 if (in) {
                     const int pl = (cy0 + r - ty0) * TILE + (x - tx0);
                     if (IS_FWD) {
@@ -876,6 +914,11 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
                     }
                 }
                 if (++x > xe) {                                       // next non-empty row of this face
+                    if (RECSPAN && ccount) {
+                        S.span[lane][cy0 + r - ty0] = (unsigned char)((cfirst << 4) | clast);
+                        irregular |= (clast - cfirst + 1 != ccount);
+                        cfirst = TILE; clast = -1; ccount = 0;
+                    }
 #pragma unroll 1
                     while (true) {
                         if (++r >= bh) { active = false; break; }
@@ -907,7 +950,10 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
         }
     }
     const unsigned nz = __ballot_sync(FULL, ncand > 0);
-    if (nz == 0u) return;
+    if (nz == 0u) {
+        if (RECSPAN && rec >= 0 && lane == 0) P.brec[(long long)rec * BREC_INTS + 1] = nb | BREC_FLAG_EMPTY;
+        return;
+    }
     mine = ncand > 0;
     const int nslots = __popc(nz);
     rank = __popc(nz & lanemask_lt());
@@ -997,6 +1043,13 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
             in = cover_slot<EXACT_DIV>(v0, v1, reinterpret_cast<const double2*>(sl)[2],
                                        (float)(tx0 + px), (float)(ty0 + py), k1, k2, w0, w1, w2);
             st.cand++;
+            if (RECSPAN && !in) {                        // a candidate of the conservative span that is not covered (~3 %)
+                // normally an end of the span (a one-pixel row is trimmed from the left, or from the right in column 15, so
+                // that no nibble overflows): remembered and applied after the walk; anything else marks the row
+                const bool left = (lx == 0) && (rlen > 1 || px < 15), right = (lx == rlen - 1);
+                if ((left || right) && (myfail >> 16) == 0u) myfail = (myfail << 16) | 1u | (ql << 1) | (py << 6) | (left ? 0u : 1u << 10);
+                else atomicOr(&S.susp[ql >> 1], (1u << py) << (16 * (ql & 1)));
+            }
         }
         if (IS_FWD) {
             if (in) {
@@ -1067,7 +1120,54 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
     }
     __syncwarp();
     if (!IS_FWD && !IS_MULTI && mine) { fm0 = S.mom[0][rank]; fa1 = S.mom[1][rank]; fa2 = S.mom[2][rank]; }
+    if (RECSPAN) {
+        // trim the conservative spans to the exact coverage (the walk is over: nobody reads the spans any more): one
+        // shared-memory add per remembered failure on the word that holds the row's byte — first column + 1 or last
+        // column - 1, neither can carry into the neighbouring byte
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned e = (myfail >> (16 * h)) & 0xffffu;
+            if (e) {
+                const unsigned q = (e >> 1) & 31u, rr = (e >> 6) & 15u;
+                atomicAdd(reinterpret_cast<unsigned*>(S.span[q]) + (rr >> 2), ((e >> 10) ? 0xffffffffu : 0x10u) << (8u * (rr & 3u)));
+            }
+        }
+        __syncwarp();
+        unsigned rows = queued ? (S.susp[lane >> 1] >> (16 * (lane & 1))) & 0xffffu : 0u;
+        // rare: rows re-derived from the hit masks, which hold the coverage of every pixel of the tile by this batch
+        while (rows) {
+            const int rr = __ffs(rows) - 1;
+            rows &= rows - 1u;
+            int first = 0, last = -1, cnt = 0;
+            for (int x = 0; x < TILE; ++x)
+                if ((S.f.hitm[rr * TILE + x] >> rank) & 1u) { if (!cnt) first = x; last = x; ++cnt; }
+            irregular |= cnt > 0 && (last - first + 1 != cnt);
+            S.span[lane][rr] = (unsigned char)(cnt > 0 ? ((first << 4) | last) : 0x10);
+        }
+    }
     }   // general path
+
+    if (RECSPAN) {
+        // the batch's exact coverage goes into its record (the spans are overwritten by the conflicted-pixel list below)
+        if (__any_sync(FULL, irregular)) {              // rare (see RasterParams::xlist)
+#ifdef CTDR_PROBE_ROWSTATS
+            if (lane == 0) atomicAdd(&g_rowstats[3], 1ull);
+#endif
+            if (irregular && queued) {
+                const int k = atomicAdd(P.xcount, 1);
+                if (k < XLIST_CAP) P.xlist[k] = make_int4(b, f, tx0, ty0);
+                else *rec_fail = 1;
+                *reinterpret_cast<uint4*>(S.span[lane]) = make_uint4(SPAN_NONE4, SPAN_NONE4, SPAN_NONE4, SPAN_NONE4);
+            }
+        }
+        if (rec >= 0 && queued) {
+            int* R = P.brec + (long long)rec * BREC_INTS;
+            R[2 + lane] = f | (fneg ? (int)0x80000000 : 0);
+            reinterpret_cast<unsigned char*>(R + BREC_INFO)[lane] = (unsigned char)((cy0 - ty0) | ((bh - 1) << 4));
+            reinterpret_cast<uint4*>(R + BREC_SPANS)[lane] = *reinterpret_cast<const uint4*>(S.span[lane]);
+        }
+        __syncwarp();
+    }
 
     if constexpr (IS_MULTI) {
         // ---- every pixel hit by the batch is (re)computed pixel-parallel for all outputs -----------
@@ -1173,9 +1273,6 @@ __device__ __forceinline__ void process_batch_blocked(const RasterParams& P, WS&
 // Faces without usable bounds (zero area, NaN, huge, two near-horizontal edges) and knife-edge rows on a
 // near-horizontal edge test every bounding-box pixel exactly.
 // ------------------------------------------------------------------------------------------
-#ifdef CTDR_PROBE_ROWSTATS
-__device__ unsigned long long g_rowstats[4];
-#endif
 constexpr int PREFIX_STRIDE = TILE + 1;
 // The prefix sums are kept in float64: a span sum is a DIFFERENCE of two prefixes, and with fp32 prefixes its
 // error would be an ulp of the whole row's running sum (measured: 2e-4 relative on grad_p6, the moments then
@@ -1189,8 +1286,7 @@ static_assert(offsetof(WarpSmem, cntv) + 64 * sizeof(int) >= 2 * TILE * PREFIX_S
 struct __align__(16) ReplayWarpSmem {
     double pre[2 * TILE * PREFIX_STRIDE];   // E0 | E1
     float  acc[TILE_PIX];                   // g (0 where no gradient)
-    int    landing[2][36];                  // the next two batch records in flight (cp.async): {next, count, 32 face ids}
-    int    qface[32];                       // faces of the current batch
+    int    landing[2][BREC_INTS];           // the current batch record and the next one in flight (cp.async, 16 B pieces)
 };
 __device__ __forceinline__ double* prefix_e0(ReplayWarpSmem& S) { return S.pre; }
 
@@ -1389,11 +1485,6 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
                     const float fs = ceilf(fmaxf(lo, xlo)), fe = floorf(fminf(hi, xhi));   // candidate columns of this row
                     // the reference's exact test must decide: the row ends when a pixel centre lies within the margin
                     // of an edge; the whole bounding-box row when the row is in doubt (see SpanSetupB::doubt)
-#ifdef CTDR_PROBE_ROWSTATS      // diagnostic build only (tools/): how many (face, row) pairs take the exact path, and why
-                    atomicAdd(&g_rowstats[0], 1ull);
-                    if ((sb.doubt >> r) & 1u) atomicAdd(&g_rowstats[1], 1ull);
-                    else if ((fs - lo < sb.din) | (hi - fe < sb.din)) { atomicAdd(&g_rowstats[2], 1ull); if (fs > fe) atomicAdd(&g_rowstats[3], 1ull); }
-#endif
                     if (((sb.doubt >> r) & 1u) | (fs - lo < sb.din) | (hi - fe < sb.din)) {
                         exact_rows |= 1u << r;
                     } else if (fs <= fe) {
@@ -1466,6 +1557,117 @@ __device__ __forceinline__ void process_batch_rows(const RasterParams& P, WS& S,
 }
 
 // ------------------------------------------------------------------------------------------
+// Backward batch of the replay kernel: lane per face, coverage READ from the batch record.
+//
+// The forward sweep recorded, per face and tile row, the interval of pixels its own exact test accepted (BREC_SPANS).
+// With the row prefix sums E0 = sum g, E1 = sum g*x' of the tile, a (face, row) pair is one byte, four shared-memory
+// loads and five float64 operations: no edge functions, no margins, no exact re-tests — the set of fragments is the
+// forward's by construction.  The moments are taken about the TILE origin in float64 (sum g, sum g*x', sum g*y') and
+// moved to the face's first corner afterwards, so nothing of the face is needed before the rows are done.
+// ------------------------------------------------------------------------------------------
+// rare: a face without a usable area (|k3| outside (1e-6, 1e10), e.g. three collinear corners): its moments are formed
+// pixel by pixel with k1, k2 exactly as the forward evaluates them — they are exact zeros where the reference's are,
+// before the 1/(k3^2 + eps) factor gets to amplify rounding
+__device__ __noinline__ float2 bwd_face_exact_moments(const double* E0, const unsigned char* spans, int r0, int nr,
+                                                      float ax, float ay, float m, float p, float n, float q, int tx0, int ty0) {
+    float A1 = 0.0f, A2 = 0.0f;
+    for (int k = 0; k < nr; ++k) {
+        const unsigned byte = spans[r0 + k];
+        const int xs = (int)(byte >> 4), xe = (int)(byte & 15u);
+        const double* row = E0 + (r0 + k) * PREFIX_STRIDE;
+        const float t = __fsub_rn((float)(ty0 + r0 + k), ay);
+        for (int x = xs; x <= xe; ++x) {
+            const float g = (float)(row[x + 1] - row[x]);
+            const float sx = __fsub_rn((float)(tx0 + x), ax);
+            A1 = fmaf(g, __fmaf_rn(sx, q, -__fmul_rn(n, t)), A1);
+            A2 = fmaf(g, __fmaf_rn(m, t, -__fmul_rn(sx, p)), A2);
+        }
+    }
+    return make_float2(A1, A2);
+}
+
+// L: the batch record in shared memory; nb faces
+template <bool GATHER, class ThreadStats>
+__device__ __forceinline__ void process_batch_spans(const RasterParams& P, ReplayWarpSmem& S, const int* L, float* gmus,
+                                                    int b, int nb, int tx0, int ty0, int lane, ThreadStats& st) {
+    const bool queued = lane < nb;
+    const unsigned char* spans = reinterpret_cast<const unsigned char*>(L + BREC_SPANS) + lane * TILE;
+    int r0 = 0, nr = 0;
+    if (queued) {
+        const unsigned info = reinterpret_cast<const unsigned char*>(L + BREC_INFO)[lane];
+        r0 = (int)(info & 15u); nr = (int)(info >> 4) + 1;
+    }
+    double M0 = 0.0, Mx = 0.0, My = 0.0;                // sum g, sum g*x', sum g*y' over the face's fragments (tile-relative)
+    typename ThreadStats::count_t nfrag{};
+    {
+        const double* E0 = prefix_e0(S);
+        const int nrmax = __reduce_max_sync(FULL, nr);
+        const unsigned char* sp = spans + r0;
+        int rowbase = r0 * PREFIX_STRIDE;
+        double yd = (double)r0;
+#pragma unroll 1
+        for (int k = 0; k < nrmax; ++k, rowbase += PREFIX_STRIDE, yd += 1.0) {
+            if (k < nr) {
+                const unsigned byte = sp[k];
+                const int xs = (int)(byte >> 4), xe = (int)(byte & 15u);
+                if (xs <= xe) {
+                    const double* q0 = E0 + rowbase + xs;
+                    const double* q1 = E0 + rowbase + xe + 1;
+                    const double d0 = q1[0] - q0[0];
+                    const double d1 = q1[TILE * PREFIX_STRIDE] - q0[TILE * PREFIX_STRIDE];
+                    M0 += d0; Mx += d1; My = fma(yd, d0, My);
+                    nfrag += (unsigned)(xe - xs + 1);
+                }
+            }
+        }
+    }
+    st.cand += nfrag; st.frag += nfrag;
+    if (queued && (M0 != 0.0 || Mx != 0.0 || My != 0.0)) {
+        const int idw = L[2 + lane];
+        const int f = idw & 0x7fffffff;
+        const long long bf = (long long)b * P.F + f;
+        float ax, ay, bx, by, cx, cy, r0l, r1l, r2l;
+        load_face<GATHER>(P, b, f, bf, ax, ay, bx, by, cx, cy, r0l, r1l, r2l);
+        const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+        const int2 lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
+        float sgn = (idw < 0) ? -1.0f : 1.0f;                         // diff_fp_for.cu:94-96 (facing bit of the record)
+        if (lab.x == lab.y) sgn = -sgn;                               // :167-169
+        // moments about the face's first corner: sum g*(x - ax), sum g*(y - ay)
+        const float m0 = (float)M0;
+        const float Ss = (float)(Mx - ((double)es.ax - (double)tx0) * M0);
+        const float St = (float)(My - ((double)es.ay - (double)ty0) * M0);
+        // the k1 / k2 moments (k1 = q*s - n*t, k2 = m*t - p*s)
+        float A1 = fmaf(es.q, Ss, -(es.n * St)), A2 = fmaf(es.m, St, -(es.p * Ss));
+        const float ak3 = fabsf(es.k3);
+        if (!((ak3 > 1e-6f) && (ak3 < 1e10f))) {
+            const float2 a = bwd_face_exact_moments(prefix_e0(S), spans, r0, nr, es.ax, es.ay, es.m, es.p, es.n, es.q, tx0, ty0);
+            A1 = a.x; A2 = a.y;
+        }
+        const float mu_in = __ldg(P.mus + lab.x), mu_out = __ldg(P.mus + lab.y);
+        const float cgeo = sgn * (mu_in - mu_out);                    // raw mu, no label-0 flip (back.cu:115)
+        float gp[6], gl[3], bsum;
+        face_grads_from_moments(es, r0l, r1l, r2l, cgeo, m0, A1, A2, gp, gl, bsum);
+        // grad_mus (back.cu:143-147): sign*(+-)bary*g for the inward label, opposite for the outward
+        st.mus_add(gmus, lab.x, (lab.x == 0 ? -sgn : sgn) * bsum, lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
+        if (P.grad_vt) {
+            // one vector RED per corner onto the corner's vertex (back.cu:126-136 and :285-292 merged)
+            const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
+            float4* gv = P.grad_vt + (long long)b * P.V;
+            atomicAdd(gv + i0, make_float4(gp[0], gp[1], gl[0], 0.0f));
+            atomicAdd(gv + i1, make_float4(gp[2], gp[3], gl[1], 0.0f));
+            atomicAdd(gv + i2, make_float4(gp[4], gp[5], gl[2], 0.0f));
+        } else {
+            float* dl = P.grad_len3 + bf * 3;                         // back.cu:126-136
+            atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
+            float* dp = P.grad_p6 + bf * 6;                           // back.cu:285-292
+#pragma unroll
+            for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
 // tile load / store helpers (one warp, 16x16 pixels, rows of 64 B)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -1516,9 +1718,11 @@ struct ReplayCtaSmem {
 };
 
 __device__ __forceinline__ void prefetch_record(const RasterParams& P, int* L, int off, int lane) {
-    const int* r = P.brec + (long long)off * BREC_INTS;
-    cp_async4(L + 2 + lane, r + 2 + lane);
-    if (lane < 2) cp_async4(L + lane, r + lane);
+    const int4* r = reinterpret_cast<const int4*>(P.brec + (long long)off * BREC_INTS);
+    int4* l = reinterpret_cast<int4*>(L);
+    static_assert(BREC_INTS % 4 == 0 && BREC_INTS / 4 <= 64, "record = at most two 16-byte pieces per lane");
+    cp_async16(l + lane, r + lane);
+    if (lane + 32 < BREC_INTS / 4) cp_async16(l + lane + 32, r + lane + 32);
 }
 
 // 8 resident CTAs (64 registers); 9 CTAs at 56 registers was measured slower (5.06 -> 6.19 ms on config 3).  Also measured
@@ -1603,28 +1807,11 @@ k_step_replay(const RasterParams P) {
                 vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
                 tt[k] = ok ? __ldg(P.target + o) : 0.0f;
             }
-            // Pipeline, two records deep: while batch k is processed, record k+1 has landed — the data of its faces
-            // (pixel box, projected vertices, lengths; in gather mode the box only: the vertex records are shared by six faces
-            // and mostly cached, and prefetching them costs a stall on the vertex ids — measured slower) is being pulled into L2 by prefetches — and record k+2 is
-            // in flight.  The kernel is latency-bound on exactly these loads (ncu: 53 % of its stall samples were
-            // long-scoreboard before); staging the face data in shared memory by cp.async instead was measured slower.
-            auto stage_faces = [&](int fid, int n) {
-                if (lane < n) {
-                    const long long bf = (long long)b * P.F + fid;
-                    prefetch_l2(P.face_box + bf);
-                    if (!GATHER) { prefetch_l2(P.p6 + bf * 6); prefetch_l2(P.p6 + bf * 6 + 5); prefetch_l2(P.len3 + bf * 3); }
-                }
-            };
-            int nbatch = 0, next = -1, id = 0, slot = 0;
-            if (roff0 >= 0) {
-                cp_async_wait_all();
-                __syncwarp();
-                const int* L0 = S.landing[0];
-                next = L0[0]; nbatch = L0[1]; id = L0[2 + lane];
-                if (next >= 0) prefetch_record(P, S.landing[1], next, lane);
-                slot = 1;
-                stage_faces(id, nbatch);                      // the first batch's faces: on their way during the g / prefix work
-            }
+            // Pipeline: while batch k is processed out of one landing zone, record k+1 is copied into the other by
+            // cp.async (16-byte pieces, no register holds the data in flight).  A record carries everything the row
+            // phase needs — face ids, rows and the exact coverage — so the only global loads left in the batch are the
+            // per-face ones of the gradient epilogue.
+            int slot = 0;
 #pragma unroll
             for (int k = 0; k < TILE / 2; ++k) {
                 float g = 0.0f;
@@ -1639,21 +1826,14 @@ k_step_replay(const RasterParams P) {
             if (roff0 < 0) continue;                                  // no face reaches this tile
             build_row_prefix(S, lane);
             while (true) {
-                if (lane < nbatch) S.qface[lane] = id;
-                const int nb_cur = nbatch;
-                const bool more = next >= 0;
-                if (more) {
-                    cp_async_wait_all();                              // record k+1, issued a whole batch ago
-                    __syncwarp();
-                    const int* L = S.landing[slot];
-                    next = L[0]; nbatch = L[1]; id = L[2 + lane];
-                    slot ^= 1;
-                    if (next >= 0) prefetch_record(P, S.landing[slot], next, lane);
-                    stage_faces(id, nbatch);
-                }
+                cp_async_wait_all();                                  // record k (issued during the prologue / a whole batch ago)
                 __syncwarp();
-                process_batch_rows<GATHER>(P, S, gmus, b, nb_cur, tx0, ty0, tx1, ty1, lane, st);
-                if (!more) break;
+                const int* L = S.landing[slot];
+                const int next = L[0], word = L[1];
+                slot ^= 1;
+                if (next >= 0) prefetch_record(P, S.landing[slot], next, lane);
+                if (!(word & BREC_FLAG_EMPTY)) process_batch_spans<GATHER>(P, S, L, gmus, b, word & 0xff, tx0, ty0, lane, st);
+                if (next < 0) break;
             }
         }
     }
@@ -1670,6 +1850,68 @@ k_step_replay(const RasterParams P) {
     if (lane == 0) {
         if (loss_acc != 0.0) atomicAdd(P.out2 + 0, loss_acc);
         if (nvalid_acc) atomicAdd(P.out2 + 1, (double)nvalid_acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual step, leftovers of the recorded coverage: one thread per listed (angle, face, tile) (RasterParams::xlist) walks
+// the face's bounding box inside the tile with the reference's exact test and the residual gradient formed on the fly —
+// the single-writer kernel's walk (k_backward_faceowner) restricted to one tile, adding with atomics.  The tile's loss
+// and valid count are the replay kernel's business.
+// ------------------------------------------------------------------------------------------
+template <bool GATHER>
+__global__ void __launch_bounds__(128)
+k_step_facelist(const RasterParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(*P.xcount, XLIST_CAP);
+    if (i >= n) return;
+    const int4 e = P.xlist[i];
+    const int b = e.x, f = e.y, tx0 = e.z, ty0 = e.w;
+    // a region that ran out of record space after this entry was listed is walked as a whole by k_raster<MODE_STEP>
+    const int rr = (ty0 / (P.RT * TILE)) * P.regions_x + tx0 / (P.RT * TILE);
+    if (P.bflag[(long long)b * (P.regions_x * P.regions_y) + rr] == 0) return;
+    const long long bf = (long long)b * P.F + f;
+    bool fneg;
+    const short4 fb = unpack_box(__ldg(P.face_box + bf), fneg);
+    const int x0 = max((int)fb.x, tx0), x1 = min((int)fb.z, min(tx0 + TILE, P.W) - 1);
+    const int y0 = max((int)fb.y, ty0), y1 = min((int)fb.w, min(ty0 + TILE, P.H) - 1);
+    float ax, ay, bx, by, cx, cy, r0, r1, r2;
+    load_face<GATHER>(P, b, f, bf, ax, ay, bx, by, cx, cy, r0, r1, r2);
+    const EdgeSetup es = edge_setup(ax, ay, bx, by, cx, cy);
+    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;
+    const long long base = (long long)b * P.H * P.W;
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) {
+            const long long o = base + (long long)y * P.W + x;
+            const float v = __ldg(P.im_in + o);
+            if (!(v > -1e-6f && v <= P.mask_hi)) continue;                       // get_valid_mask (fp_vecs.py:10-13)
+            const float g = 2.0f * (v - __ldg(P.target + o));
+            if (g == 0.0f) continue;
+            float s, t, k1, k2, w0, w1, w2;
+            if (!cover_exact<true>(es, (float)x, (float)y, s, t, k1, k2, w0, w1, w2)) continue;
+            M0 += g; A1 = fmaf(g, k1, A1); A2 = fmaf(g, k2, A2);
+        }
+    if (M0 == 0.0f && A1 == 0.0f && A2 == 0.0f) return;
+    const int2 lab = __ldg(reinterpret_cast<const int2*>(P.labels2) + f);
+    float sgn = fneg ? -1.0f : 1.0f;                                              // diff_fp_for.cu:94-96
+    if (lab.x == lab.y) sgn = -sgn;                                               // :167-169
+    const float cgeo = sgn * (__ldg(P.mus + lab.x) - __ldg(P.mus + lab.y));       // raw mu, no label-0 flip (back.cu:115)
+    float gp[6], gl[3], bsum;
+    face_grads_from_moments(es, r0, r1, r2, cgeo, M0, A1, A2, gp, gl, bsum);
+    atomicAdd(P.grad_mus + lab.x, (lab.x == 0 ? -sgn : sgn) * bsum);              // back.cu:143-147
+    atomicAdd(P.grad_mus + lab.y, (lab.y == 0 ? sgn : -sgn) * bsum);
+    if (P.grad_vt) {
+        const int i0 = __ldg(P.faces + 3 * f), i1 = __ldg(P.faces + 3 * f + 1), i2 = __ldg(P.faces + 3 * f + 2);
+        float4* gv = P.grad_vt + (long long)b * P.V;
+        atomicAdd(gv + i0, make_float4(gp[0], gp[1], gl[0], 0.0f));
+        atomicAdd(gv + i1, make_float4(gp[2], gp[3], gl[1], 0.0f));
+        atomicAdd(gv + i2, make_float4(gp[4], gp[5], gl[2], 0.0f));
+    } else {
+        float* dl = P.grad_len3 + bf * 3;
+        atomicAdd(dl + 0, gl[0]); atomicAdd(dl + 1, gl[1]); atomicAdd(dl + 2, gl[2]);
+        float* dp = P.grad_p6 + bf * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(dp + k, gp[k]);
     }
 }
 
@@ -1940,6 +2182,7 @@ k_raster(const RasterParams P) {
             const short4* fbrow = P.face_box + (long long)b * P.F;
             while (true) {
                 int nbatch;
+                bool rec_now = false;                          // recording: this batch found record space
                 if (replay) {
                     // the forward sweep already found this tile's faces and cut them into batches
                     if (roff < 0) break;
@@ -2002,9 +2245,9 @@ k_raster(const RasterParams P) {
                     if (lane == 0) off = atomicAdd(P.bcursor + b, 1);
                     off = __shfl_sync(FULL, off, 0);
                     if (off < P.bcap) {
+                        rec_now = true;
                         off += b * P.bcap;
-                        int* r = P.brec + (long long)off * BREC_INTS;
-                        if (lane < nbatch) r[2 + lane] = S.qface[lane];
+                        int* r = P.brec + (long long)off * BREC_INTS;       // face ids, rows and coverage: process_batch_blocked
                         if (lane == 0) {
                             r[0] = -1; r[1] = nbatch;
                             if (roff >= 0) P.brec[(long long)roff * BREC_INTS] = off;     // link behind the previous record
@@ -2020,7 +2263,8 @@ k_raster(const RasterParams P) {
                 else if (K_BWD) {
                     if (!prefix_ready) { build_row_prefix(S, lane); prefix_ready = true; }
                     process_batch_rows<GATHER>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
-                } else process_batch_blocked<MODE, EXACT_DIV, DIRECT, GATHER>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st);
+                } else process_batch_blocked<MODE, EXACT_DIV, DIRECT, GATHER, RECORD>(P, S, gmus, b, nbatch, tx0, ty0, tx1, ty1, lane, st,
+                                                                                          rec_now ? roff : -1, &C.rec_fail);
                 if (!replay) {
                     const int rest = qn - nbatch;              // < 32: shift the tail to the front
                     int tf = 0;

@@ -19,4 +19,4 @@ torch.cuda.synchronize()
 out = (ctypes.c_ulonglong * 4)()
 h.ctdr_debug_rowstats(out, 0)
 rows, doubt, margin, empty = list(out)
-print(f"(face,row) pairs {rows}: exact by doubt {doubt} ({100*doubt/rows:.3f} %), by margin {margin} ({100*margin/rows:.3f} %), of which empty rows {empty}")
+print("batches", rows, "irregular faces", doubt, "-", margin, "irregular batches", empty)
