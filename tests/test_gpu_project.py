@@ -308,7 +308,46 @@ def test_full_size_config3_properties(cuda_lib):
     assert float(gv.norm()) > 0
 
 
+def nasty_mesh():
+    """A sphere plus what the recorded coverage has to survive: zero-area faces (repeated and collinear corners), long
+    slivers a fraction of a pixel thick (their rows have no usable span bounds, most candidates of a row fail), faces
+    that span many tiles, and a fan of needle faces around one vertex."""
+    verts, faces, labels, mus = cases.sphere_mesh(2, 0.45)
+    rng = np.random.default_rng(11)
+    V0 = verts.shape[0]
+    extra_v, extra_f = [], []
+
+    def add(tri):
+        base = V0 + len(extra_v)
+        extra_v.extend(tri)
+        extra_f.append([base, base + 1, base + 2])
+
+    for _ in range(30):                                   # slivers: 0.6 long, 1e-4 .. 3e-3 thick, any orientation
+        p = rng.uniform(-0.4, 0.4, 3); d = rng.normal(size=3); d /= np.linalg.norm(d)
+        n = np.cross(d, rng.normal(size=3)); n /= np.linalg.norm(n)
+        add([p, p + 0.6 * d, p + 0.6 * d + rng.uniform(1e-4, 3e-3) * n])
+    for _ in range(10):                                   # collinear corners: exactly zero area in world space
+        p = rng.uniform(-0.4, 0.4, 3); d = rng.normal(size=3) * 0.2
+        add([p, p + d, p + 2 * d])
+    for _ in range(6):                                    # big faces over many tiles
+        add(list(rng.uniform(-0.6, 0.6, (3, 3))))
+    c = rng.uniform(-0.2, 0.2, 3)                         # needle fan
+    for k in range(24):
+        a0, a1 = 2 * np.pi * k / 24, 2 * np.pi * (k + 0.02) / 24
+        add([c, c + 0.5 * np.array([np.cos(a0), np.sin(a0), 0.3]), c + 0.5 * np.array([np.cos(a1), np.sin(a1), 0.3])])
+    nv = np.concatenate([verts, np.asarray(extra_v, np.float32)]).astype(np.float32)
+    nf = np.concatenate([faces, np.asarray(extra_f, faces.dtype)])
+    for i in range(0, 40, 2):                             # repeated corners on existing vertices
+        nf = np.concatenate([nf, np.asarray([[i, i, i + 1], [i, i + 1, i + 1]], faces.dtype)])
+    nl = np.tile(np.array([1, 0], labels.dtype), (nf.shape[0], 1))
+    return nv, nf, nl, mus
+
+
 LINK_CASES = {
+    # degenerate, sliver and oversized faces: rows re-derived from the hit masks, faces listed for k_step_facelist,
+    # zero-area faces in the replay epilogue
+    "nasty_parallel": lambda: (cases.parallel_geometry(6, 160), nasty_mesh()),
+    "nasty_cone": lambda: (cases.cone_geometry(6, 160), nasty_mesh()),
     # ordinary case: everything is recorded and replayed
     "two_material": lambda: (cases.cone_geometry(5, 160), cases.two_material_mesh(2)),
     # 100k faces on a 128 x 128 detector: region lists take several segments, chains continue across them
@@ -344,5 +383,9 @@ def test_linked_sweeps_equal_unlinked(cuda_lib, monkeypatch, name):
         _, _, st = R.project_forward(gd, v, f32, labels, mus, idx, want_stats=True)
         assert st[3].item() > 0
     assert o0[1].item() == o1[1].item() and abs(o0[0].item() - o1[0].item()) <= 1e-12 * abs(o0[0].item())
-    assert (gv1 - gv0).norm().item() <= 2e-5 * gv0.norm().item() and gv0.norm().item() > 0
-    assert (gm1 - gm0).norm().item() <= 2e-5 * gm0.norm().item()
+    assert torch.isfinite(gv1).all() and torch.isfinite(gm1).all()
+    rel_v = (gv1 - gv0).norm().item() / gv0.norm().item()
+    rel_m = (gm1 - gm0).norm().item() / gm0.norm().item()
+    print(f"[{name}] linked vs unlinked residual step: grad_verts rel {rel_v:.2e}, grad_mus rel {rel_m:.2e}")
+    assert rel_v <= 2e-5 and gv0.norm().item() > 0
+    assert rel_m <= 2e-5
