@@ -27,18 +27,22 @@ MARKERS = [
     ("    const unsigned nz = __ballot_sync(FULL, ncand > 0);", "batch: prefix sums, slot staging, range search"),
     ("    float M0 = 0.0f, A1 = 0.0f, A2 = 0.0f;", "candidate loop (walk + accumulate)"),
     ("        // Faces split over several lanes:", "backward: merge of partial moments"),
-    ("    if (IS_MULTI) {\n", "hit-mask check / fix-up / per-face RED"),
+    ("    if (RECSPAN) {\n        // trim the conservative spans", "recording: trim spans to the exact coverage"),
+    ("    if (RECSPAN) {\n        // the batch's exact coverage goes into its record", "recording: coverage -> batch record"),
+    ("    if constexpr (IS_MULTI) {", "hit-mask check / fix-up / per-face RED"),
     ("constexpr int PREFIX_STRIDE = TILE + 1;", "backward rows: prefix sums of g"),
     ("struct SpanSetupB {", "backward rows: span set-up"),
     ("__device__ __noinline__ float4 bwd_row_exact(", "backward rows: exact rows (rare)"),
     ("__device__ __forceinline__ void process_batch_rows(", "backward rows: face loads + edge set-up"),
-    ("            for (int r = 0; r < bhmax; ++r, t += 1.0f, rowbase += PREFIX_STRIDE) {", "backward rows: row loop"),
+    ("            for (int r = 0; r < bhmax; ++r, rf += 1.0f, rowbase += PREFIX_STRIDE) {", "backward rows: row loop"),
     ("        if (__any_sync(FULL, exact_rows != 0u)) {", "backward rows: exact-row dispatch"),
     ("    st.cand += nfrag; st.frag += nfrag;", "backward rows: per-face gradients + RED"),
+    ("// Backward batch of the replay kernel: lane per face, coverage READ from the batch record.", "replay batch: rows from recorded coverage"),
+    ("    st.cand += nfrag; st.frag += nfrag;\n    if (queued && (M0 != 0.0", "replay batch: per-face gradients + RED"),
     ("// tile load / store helpers", "tile loads / stores"),
     ("struct ReplayCtaSmem {", "replay kernel: prologue, empty regions"),
     ("        const int tiles_x = (P.W + TILE - 1) / TILE, tiles_y = (P.H + TILE - 1) / TILE;\n        const int ntiles", "replay kernel: tile dispatch + residual prologue"),
-    ("            auto stage_faces = [&](int fid, int n) {", "replay kernel: record pipeline + prefetch"),
+    ("            // Pipeline: while batch k is processed out of one landing zone", "replay kernel: g tile, prefix sums, record pipeline"),
     ("    st.mus_flush(gmus);\n    __syncthreads();\n    for (int k = tid; k < P.n_mus; k += THREADS) {\n        const float v = gmus[k];\n        if (v != 0.0f) atomicAdd(P.grad_mus + k, v);\n    }\n    // masked L2", "replay kernel: tail"),
     ("k_raster(const RasterParams P) {", "kernel prologue + shared-address rebuilds"),
     ("        // ---- phase A:", "phase A (region list) + empty regions"),
@@ -73,11 +77,11 @@ def main(rep, lib, src_path):
         return name
 
     # the two kernels of the residual step: forward (records batches) and the replay-only residual/backward
-    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1, (bool)1", "k_rasterILi0ELb0ELb0ELb0ELb1ELb1"),
-                           ("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1>", "k_rasterILi0ELb0ELb0ELb0ELb1EE"),
+    for ksub_ncu, ksub in (("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1>", "k_rasterILi0ELb0ELb0ELb0ELb1EE"),
                            ("k_raster<(int)3, (bool)0, (bool)0, (bool)0, (bool)1", "k_rasterILi3ELb0ELb0ELb0ELb1"),
                            ("k_step_replay<(bool)0, (bool)1", "k_step_replayILb0ELb1"),
-                           ("k_step_replay<(bool)0>", "k_step_replayILb0EE")):
+                           ("k_step_replay<(bool)0>", "k_step_replayILb0EE"),
+                           ("k_raster<(int)0, (bool)0, (bool)0, (bool)0, (bool)1, (bool)1, (bool)1", "k_rasterILi0ELb0ELb0ELb0ELb1ELb1ELb1")):
         try:
             blk = S.ncu_rows(rep, ksub_ncu)
         except SystemExit:
