@@ -295,6 +295,8 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
     launches0 = L.ctdr_launch_count()
     ms_step = D.timed_device(step, args.steps)
     launches = (L.ctdr_launch_count() - launches0) + args.steps * xch.kernels_per_exchange(world)
+    if xch.peer is not None:
+        assert xch.peer.status() == 0, "peer all-reduce gave up waiting for a rank: the sums are invalid"
     clocks = sampler.stop() if rank == 0 else None
     pixels = NA * H * W
     value = pixels / (ms_step / 1e3) / 1e9
@@ -370,6 +372,10 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
     if not args.no_breakdown and rank == 0:
         staged = staged_breakdown(torch, R, gd, verts, faces32, labels, mus, idx, target)
 
+    collective = xch.collective
+    if xch.peer is not None:
+        assert xch.peer.status() == 0, "peer all-reduce gave up waiting for a rank"
+        xch.peer.close(); xch.peer = None                     # collective: every rank unmaps before anyone frees
     if rank != 0:
         return None
 
@@ -387,7 +393,8 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
                        "step": "projection + masked-L2 residual + backward over all angles + gradient all-reduce",
                        "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)" if Bl * H * W * 8 > 2 * 126e6
                                     else "inputs smaller than L2: the step streams its own 2 x B x H x W x 4 B of sinogram/target, nothing else is reused between steps",
-                       "parallelism": f"angles sharded over {world} GPU(s) (rank r owns angles r, r+N, ...), mesh replicated"},
+                       "parallelism": f"angles sharded over {world} GPU(s) (rank r owns angles r, r+N, ...), mesh replicated",
+                       "collective": collective},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches) * world,
             "gpu_launches_per_rank_per_step": launches / args.steps,
             "loss": loss_sum / max(n_valid, 1.0), "n_valid": n_valid}

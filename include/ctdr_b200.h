@@ -8,15 +8,16 @@
  *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer on the current
  *     CUDA device unless its name ends in `_host`;
  *   - the caller owns and allocates every buffer (as in the reference, diff_fp.cpp:21-26 /
- *     rasterizer.py:36-46); the library allocates nothing. Scratch memory is a caller-provided
+ *     rasterizer.py:36-46); the library allocates nothing (one exception: ctdr_peer_block_create, whose
+ *     memory must be exportable through CUDA IPC). Scratch memory is a caller-provided
  *     `workspace` whose size comes from the matching `*_workspace_bytes` query;
  *   - work is enqueued on `stream` (a cudaStream_t) and returns without synchronising
  *     (the reference launches on the legacy default stream: diff_fp_for.cu:253);
  *   - return value: 0 ok, < 0 argument error (CTDR_E_*), > 0 a cudaError_t; a thread-local
  *     message is available from ctdr_last_error();
  *   - re-entrant, no global state besides that thread-local string;
- *   - fp32 only on the device (the reference also dispatches double, diff_fp_for.cu:251; the
- *     fp64 instantiation lives in the CPU oracle as the high-precision referee);
+ *   - float32 entry points are the tuned path; the reference also dispatches double (diff_fp_for.cu:251):
+ *     the *_f64 entry points below are that instantiation on the device;
  *   - sinogram / counts are [B,H,W] row-major (the reference's [B,H,W,1]); pixel offsets are 64-bit.
  *
  * Deviations from the reference kernels, all documented in DESIGN.md:
@@ -36,8 +37,9 @@
 extern "C" {
 #endif
 
-#define CTDR_ABI_VERSION 4   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi; 3: + ctdr_launch_count,
-                                ctdr_project_residual_step_timed; 4: + the float64 instantiation (*_f64) */
+#define CTDR_ABI_VERSION 5   /* 2: + ctdr_raster_forward_multi, ctdr_project_forward_multi; 3: + ctdr_launch_count,
+                                ctdr_project_residual_step_timed; 4: + the float64 instantiation (*_f64);
+                                5: + peer blocks and the one-launch NVLink all-reduce (ctdr_peer_*) */
 
 /* argument errors */
 #define CTDR_E_NULL      (-1)   /* a required pointer is NULL */
@@ -307,6 +309,35 @@ int ctdr_project_residual_step_timed(int geom_kind, const float* geom, int nangl
                                      void* workspace, size_t workspace_bytes,
                                      int64_t* stats, unsigned flags, ctdr_stream_t stream,
                                      float* stage_ms_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU exchange of the angle-sharded residual step (the reference has no distributed code; this is the
+ * one collective of the path: SUM over ranks of [grad_verts | grad_mus] and {loss_sum, n_valid}).
+ * One process per GPU.  Every rank creates a peer block, hands its 64-byte IPC handle to the other ranks (any
+ * transport: torch.distributed.all_gather_object, MPI, a file), opens theirs, and then sums a local payload
+ * over all ranks with ONE kernel launch that reads the peers' blocks over NVLink (one-shot all-reduce; sized
+ * for payloads up to a few MB, i.e. meshes up to ~500k vertices — use a library all-reduce beyond that).
+ * Sums are formed in rank order on every rank: all ranks end with bit-identical results.
+ * ------------------------------------------------------------------------------------------- */
+#define CTDR_PEER_HANDLE_BYTES 64
+#define CTDR_PEER_MAX_RANKS    8
+/* device bytes behind a peer block for payloads of up to payload_bytes (header + two payload slots) */
+size_t ctdr_peer_block_bytes(size_t payload_bytes);
+/* cudaMalloc + zero a peer block on the current device; handle_host (64 bytes, HOST memory, may be NULL when all
+ * ranks live in one process) receives its CUDA IPC handle.  Synchronises the device once. */
+int ctdr_peer_block_create(size_t payload_bytes, void** block, unsigned char* handle_host);
+/* map another process's peer block into this one (peer access is enabled on demand) / unmap it */
+int ctdr_peer_block_open(const unsigned char* handle_host, void** block);
+int ctdr_peer_block_close(void* block);
+int ctdr_peer_block_destroy(void* block);
+/* 0 = fine, 1 = some launch gave up waiting for a peer (> ~2 s): its sums are invalid.  Sticky; synchronous copy. */
+int ctdr_peer_block_status(const void* block, int* status_host);
+/* local (device, 16-byte aligned) = f32_bytes of float32 followed by f64_bytes of float64 (both multiples of 16,
+ * together <= the payload_bytes the blocks were created with); overwritten by the sums over all ranks.
+ * blocks_host[r] = rank r's peer block as mapped in this process (blocks_host[rank] = the one this rank created).
+ * Every rank must make the same sequence of calls with the same sizes.  Enqueued on `stream`; capturable. */
+int ctdr_peer_allreduce(void* const* blocks_host, int world, int rank, size_t payload_bytes,
+                        void* local, size_t f32_bytes, size_t f64_bytes, ctdr_stream_t stream);
 
 #ifdef __cplusplus
 }

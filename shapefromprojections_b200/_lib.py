@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("CTDR_LIB") or os.path.join(_HERE, "csrc", "libctdr_b2
 
 FLAG_NO_PREFILTER = 1
 FLAG_DETERMINISTIC = 2
-ABI_VERSION = 4          # include/ctdr_b200.h: CTDR_ABI_VERSION
+ABI_VERSION = 5          # include/ctdr_b200.h: CTDR_ABI_VERSION
 STAT_NONPOSITIVE_LEN, STAT_FRAGMENTS, STAT_CANDIDATES, STAT_LIST_SEGMENTS, STAT_COUNT = 0, 1, 2, 3, 8
 GEOM_PARALLEL3D, GEOM_PARALLEL3D_VEC, GEOM_CONE_VEC = 0, 1, 2
 GEOM_KINDS = {"parallel3d": GEOM_PARALLEL3D, "parallel3d_vec": GEOM_PARALLEL3D_VEC, "cone_vec": GEOM_CONE_VEC}
@@ -53,6 +53,13 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp]),
     "ctdr_project_residual_step_timed": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _d, _d, _d,
                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _u, _vp, _vp]),
+    "ctdr_peer_block_bytes": (_sz, [_sz]),
+    "ctdr_peer_block_create": (_i, [_sz, _vp, _vp]),
+    "ctdr_peer_block_open": (_i, [_vp, _vp]),
+    "ctdr_peer_block_close": (_i, [_vp]),
+    "ctdr_peer_block_destroy": (_i, [_vp]),
+    "ctdr_peer_block_status": (_i, [_vp, _vp]),
+    "ctdr_peer_allreduce": (_i, [_vp, _i, _i, _sz, _vp, _sz, _sz, _vp]),
 }
 STAGES = ("vertex_forward", "raster_forward", "memset", "raster_step", "vertex_backward")   # CTDR_STAGE_*
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libctdr_b200.so")
 SOURCES = ["ctdr_b200.cu"]
-DEPS = ["ctdr_common.cuh", "ctdr_raster.cuh", "ctdr_vertex.cuh", "ctdr_raster64.cuh", "ctdr_vertex64.cuh", os.path.join(REPO, "include", "ctdr_b200.h")]
+DEPS = ["ctdr_common.cuh", "ctdr_raster.cuh", "ctdr_vertex.cuh", "ctdr_raster64.cuh", "ctdr_vertex64.cuh", "ctdr_peer.cuh", os.path.join(REPO, "include", "ctdr_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]

@@ -6,6 +6,7 @@
 #include "ctdr_vertex.cuh"
 #include "ctdr_raster64.cuh"
 #include "ctdr_vertex64.cuh"
+#include "ctdr_peer.cuh"
 
 #include <atomic>
 #include <cstdarg>
@@ -1167,6 +1168,84 @@ int ctdr_project_residual_step_timed(int geom_kind, const float* geom, int nangl
     tm.collect(stage_ms_host, CTDR_STAGE_COUNT);          // synchronises with the last recorded event
     if (rc) return rc;
     if (!ok) return fail(CTDR_E_SHAPE, "ctdr_project_residual_step_timed: more than %d stage marks (too many angle windows)", StageTimer::MAX_MARKS);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer blocks + the one-launch all-reduce over NVLink peer memory (ctdr_peer.cuh)
+// ---------------------------------------------------------------------------------------------
+static_assert(CTDR_PEER_HANDLE_BYTES == sizeof(cudaIpcMemHandle_t), "IPC handle size");
+static_assert(CTDR_PEER_MAX_RANKS == PEER_MAX_RANKS, "kernel and ABI disagree on the rank count");
+
+static size_t peer_slot_bytes(size_t payload_bytes) { return align_up(payload_bytes, 256); }
+
+size_t ctdr_peer_block_bytes(size_t payload_bytes) { return PEER_HEADER_BYTES + 2 * peer_slot_bytes(payload_bytes); }
+
+int ctdr_peer_block_create(size_t payload_bytes, void** block, unsigned char* handle_host) {
+    if (!block) return fail(CTDR_E_NULL, "ctdr_peer_block_create: block is NULL");
+    if (payload_bytes == 0 || (payload_bytes & 15)) return fail(CTDR_E_SHAPE, "ctdr_peer_block_create: payload_bytes=%zu must be a positive multiple of 16", payload_bytes);
+    void* p = nullptr;
+    const size_t n = ctdr_peer_block_bytes(payload_bytes);
+    CTDR_CUDA(cudaMalloc(&p, n), "cudaMalloc(peer block)");
+    cudaError_t e = cudaMemset(p, 0, n);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && handle_host) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e == cudaSuccess) memcpy(handle_host, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "ctdr_peer_block_create"); }
+    *block = p;
+    return 0;
+}
+
+int ctdr_peer_block_open(const unsigned char* handle_host, void** block) {
+    if (!handle_host || !block) return fail(CTDR_E_NULL, "ctdr_peer_block_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    CTDR_CUDA(cudaIpcOpenMemHandle(block, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    return 0;
+}
+
+int ctdr_peer_block_close(void* block) {
+    if (!block) return 0;
+    CTDR_CUDA(cudaIpcCloseMemHandle(block), "cudaIpcCloseMemHandle");
+    return 0;
+}
+
+int ctdr_peer_block_destroy(void* block) {
+    if (!block) return 0;
+    CTDR_CUDA(cudaFree(block), "cudaFree(peer block)");
+    return 0;
+}
+
+int ctdr_peer_block_status(const void* block, int* status_host) {
+    if (!block || !status_host) return fail(CTDR_E_NULL, "ctdr_peer_block_status: NULL argument");
+    unsigned v = 0;
+    CTDR_CUDA(cudaMemcpy(&v, static_cast<const unsigned*>(block) + PEER_CTL_STATUS, sizeof(v), cudaMemcpyDeviceToHost), "ctdr_peer_block_status");
+    *status_host = (int)v;
+    return 0;
+}
+
+int ctdr_peer_allreduce(void* const* blocks_host, int world, int rank, size_t payload_bytes,
+                        void* local, size_t f32_bytes, size_t f64_bytes, ctdr_stream_t stream) {
+    if (!blocks_host || !local) return fail(CTDR_E_NULL, "ctdr_peer_allreduce: NULL argument");
+    if (world < 1 || world > PEER_MAX_RANKS || rank < 0 || rank >= world)
+        return fail(CTDR_E_SHAPE, "ctdr_peer_allreduce: world=%d rank=%d (at most %d ranks)", world, rank, PEER_MAX_RANKS);
+    if ((f32_bytes & 15) || (f64_bytes & 15) || f32_bytes + f64_bytes == 0 || f32_bytes + f64_bytes > payload_bytes || (reinterpret_cast<uintptr_t>(local) & 15))
+        return fail(CTDR_E_SHAPE, "ctdr_peer_allreduce: f32_bytes=%zu f64_bytes=%zu must be multiples of 16 within payload_bytes=%zu, local 16-byte aligned", f32_bytes, f64_bytes, payload_bytes);
+    PeerTable T = {};
+    for (int r = 0; r < world; ++r) {
+        if (!blocks_host[r]) return fail(CTDR_E_NULL, "ctdr_peer_allreduce: block of rank %d is NULL", r);
+        T.block[r] = static_cast<unsigned char*>(blocks_host[r]);
+    }
+    const long long nvec = (long long)((f32_bytes + f64_bytes) / 16);
+    int slices = (int)((nvec + 2 * PEER_THREADS - 1) / (2 * PEER_THREADS));     // about two vectors per thread
+    slices = slices < 1 ? 1 : (slices > PEER_MAX_SLICES ? PEER_MAX_SLICES : slices);
+    k_peer_allreduce<<<slices, PEER_THREADS, 0, (cudaStream_t)stream>>>(T, world, rank, static_cast<float4*>(local),
+                                                                        (long long)(f32_bytes / 16), (int)(f64_bytes / 16),
+                                                                        peer_slot_bytes(payload_bytes));
+    CTDR_LAUNCHED(1, "k_peer_allreduce");
     return 0;
 }
 

@@ -44,7 +44,8 @@ def projection_step(model, idx_angles, p_batch, exchange=None):
     mus = model.mus.detach().contiguous()
     dev = verts.device
     if exchange is None:
-        exchange = distributed.GradientExchange(verts.shape[0], mus.numel(), dev)
+        # ad-hoc buffers: no peer blocks (setting those up is a collective and worth it only for a persistent exchange)
+        exchange = distributed.GradientExchange(verts.shape[0], mus.numel(), dev, peer=False)
     exchange.zero_()
     idx = R._device_idx(idx_angles, dev, fp.geom.nangles)
     phat, _, _, _ = R.project_residual_step(fp.geom, verts, fp._faces32(model.faces), fp.labels_fx2, mus, idx,

@@ -40,8 +40,22 @@ xch = distributed.GradientExchange(v.shape[0], mus.numel(), dev)
 xch.zero_()
 ph, _, _, _ = R.project_residual_step(gd, v, f32, lab, mus, mine, target_full[mine].contiguous(),
                                       grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
+local_copy = xch.storage.clone()
 xch.all_reduce()
 torch.cuda.synchronize()
+# the exchange ran as the library's own kernel over NVLink peer memory (CUDA IPC between the two processes) ...
+assert xch.peer is not None, "peer all-reduce was not set up: " + xch.collective
+assert xch.peer.status() == 0
+# ... and agrees bit for bit with the NCCL all-reduce of the same local buffers (two ranks: a + b either way)
+nccl = distributed.GradientExchange(v.shape[0], mus.numel(), dev, peer=False)
+nccl.storage.copy_(local_copy)
+nccl.all_reduce()
+torch.cuda.synchronize()
+assert torch.equal(nccl.storage, xch.storage), "peer all-reduce differs from NCCL"
+for _ in range(3):                                              # repeated use: both payload slots, epochs in step
+    xch.storage.copy_(local_copy); xch.all_reduce()
+torch.cuda.synchronize()
+assert torch.equal(nccl.storage, xch.storage) and xch.peer.status() == 0
 assert torch.equal(ph, ph1[mine]), "sinogram shard differs from the one-rank slices"
 assert xch.scalars[1].item() == o1[1].item(), (xch.scalars.tolist(), o1.tolist())
 assert abs(xch.scalars[0].item() - o1[0].item()) <= 1e-9 * o1[0].item()
@@ -50,6 +64,7 @@ assert ev <= 1e-5 and em <= 1e-5, (ev, em)
 assert gv1.norm().item() > 0
 gv, gm, loss = xch.mean_gradients()
 assert abs(loss.item() - o1[0].item() / o1[1].item()) <= 1e-9 * loss.item()
+xch.peer.close()
 dist.barrier(); dist.destroy_process_group()
 sys.stdout.write(f"rank {{rank}} ok grad_verts rel {{ev:.2e}} grad_mus rel {{em:.2e}}\n"); sys.stdout.flush()
 """

@@ -31,7 +31,7 @@ def test_shared_library_exports_every_declared_symbol():
         n = 0 if params.strip() in ("", "void") else params.count(",") + 1
         assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
     handle.ctdr_abi_version.restype = ctypes.c_int
-    assert handle.ctdr_abi_version() == _lib.ABI_VERSION == 4
+    assert handle.ctdr_abi_version() == _lib.ABI_VERSION == 5
     # argument validation happens before any CUDA call: usable without a device
     _lib.lib()
     rc = _lib.lib().ctdr_raster_forward(None, None, None, None, None, 1, 1, 1, 8, 8, 1.0, None, None, None, 0, None, 0, None)
