@@ -85,6 +85,7 @@ struct Tuning {
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
+    int face_normals = 1;        // CTDR_FACE_NORMALS: 0 = k_face_assemble forms the face normal and the unit ray per (angle, face) again
     int gather = 1;              // CTDR_GATHER: 1 = fused raster kernels gather corners from the per-vertex records (no p6/len3/ff), 0 = face arrays     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
     void load() {
         *this = Tuning();
@@ -94,6 +95,7 @@ struct Tuning {
         no_batch_records = getenv("CTDR_NO_BATCH_RECORDS") != nullptr;
         if (const char* e = getenv("CTDR_GRAD_PER_VERTEX")) grad_per_vertex = atoi(e);
         if (const char* e = getenv("CTDR_GATHER")) gather = atoi(e) != 0;
+        if (const char* e = getenv("CTDR_FACE_NORMALS")) face_normals = atoi(e) != 0;
     }
 };
 Tuning& tuning() {
@@ -499,6 +501,7 @@ struct ProjectWs {
     float *p6, *len3, *ff, *gp6, *glen3;
     float4* gvt;         // [window, V] per-vertex cotangents of the raster backward (default backward)
     float4* vt;          // [window, V] per-vertex transform records
+    float4* fnorm;       // [F] world-space face normals (k_face_normals), gather mode of the *_VEC geometries
     AngleConst* atab;    // [window] per-angle constants of the vertex stage
     float* fs;           // [window, F] per-face attenuation terms (deterministic backward)
     double* partials;    // [2 * DET_LOSS_BLOCKS] (deterministic residual)
@@ -534,8 +537,14 @@ size_t project_per_angle_bytes(int V, int F, bool bwd, int H = 0, int W = 0, boo
            MAX_SR * MAX_SR * sizeof(int) + sizeof(AngleConst) + 512;
 }
 
+// window-independent part of the fused projector's workspace: alignment padding, the irregular-face list, the
+// deterministic loss partials and the per-face normals
+size_t project_fixed_bytes(int F) {
+    return 32 * 256 + XLIST_CAP * sizeof(int4) + 2 * DET_LOSS_BLOCKS * sizeof(double) + align_up((size_t)F * sizeof(float4), 256);
+}
+
 int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, size_t bytes, ProjectWs* ws, bool face_arrays = true) {
-    const size_t slack = 32 * 256 + XLIST_CAP * sizeof(int4) + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    const size_t slack = project_fixed_bytes(F);
     const size_t per = project_per_angle_bytes(V, F, bwd, H, W, face_arrays);
     if (bytes < per + slack) return fail(CTDR_E_WORKSPACE, "workspace %zu B < one angle (%zu B)", bytes, per + slack);
     long long win = (long long)((bytes - slack) / per);
@@ -546,6 +555,7 @@ int project_ws_layout(int B, int V, int F, int H, int W, bool bwd, void* base, s
     ws->window = (int)win;
     char* p = static_cast<char*>(base);
     size_t off = 0;
+    ws->fnorm = reinterpret_cast<float4*>(p + off); off += align_up((size_t)F * sizeof(float4), 256);
     ws->vt = reinterpret_cast<float4*>(p + off);  off += align_up((size_t)win * V * sizeof(float4), 256);
     ws->atab = reinterpret_cast<AngleConst*>(p + off); off += align_up((size_t)win * sizeof(AngleConst), 256);
     ws->p6 = ws->len3 = ws->ff = nullptr;
@@ -601,7 +611,7 @@ int launch_angle_table(VertexParams& P, AngleConst* tab, cudaStream_t st) {
 // vertex stage of one angle window in the fused path; also produces the face and chunk pixel boxes
 // full = false: boxes only — the raster kernels gather the corners from `vt` (RasterParams::vt)
 int launch_vertex_forward_staged(const VertexParams& P, float4* vt, const int32_t* labels2, float* p6, float* len3, float* ff,
-                                 short4* face_boxes, short4* chunk_boxes, cudaStream_t st, bool full = true) {
+                                 short4* face_boxes, short4* chunk_boxes, cudaStream_t st, bool full = true, float4* fnorm = nullptr) {
     const long long nv = (long long)P.B * P.V;
     if ((nv + 255) / 256 > 0x7fffffffLL) return fail(CTDR_E_SHAPE, "B*V too large for one launch");
     if (P.B > 65535) return fail(CTDR_E_SHAPE, "angle window of %d angles > 65535", P.B);
@@ -609,7 +619,14 @@ int launch_vertex_forward_staged(const VertexParams& P, float4* vt, const int32_
     CTDR_LAUNCHED(1, "k_vertex_transform launch");
     const dim3 grid((unsigned)((P.F + 255) / 256), (unsigned)P.B);
     if (full) k_face_assemble<true><<<grid, 256, 0, st>>>(P, vt, labels2, p6, len3, ff, face_boxes, chunk_boxes);
-    else k_face_assemble<false><<<grid, 256, 0, st>>>(P, vt, labels2, nullptr, nullptr, nullptr, face_boxes, chunk_boxes);
+    else {
+        if (P.kind == 0 || !tuning().face_normals) fnorm = nullptr;
+        if (fnorm) {
+            k_face_normals<<<(unsigned)((P.F + 255) / 256), 256, 0, st>>>(P.verts, P.faces, P.F, fnorm);
+            CTDR_LAUNCHED(1, "k_face_normals launch");
+        }
+        k_face_assemble<false><<<grid, 256, 0, st>>>(P, vt, labels2, nullptr, nullptr, nullptr, face_boxes, chunk_boxes, fnorm);
+    }
     CTDR_LAUNCHED(1, "k_face_assemble launch");
     return 0;
 }
@@ -912,7 +929,7 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + 32 * 256 + XLIST_CAP * sizeof(int4) + 2 * DET_LOSS_BLOCKS * sizeof(double);
+    return per * (size_t)win + project_fixed_bytes(F);
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -933,7 +950,7 @@ int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const in
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather, ws.fnorm)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
         P.im = im + (size_t)b0 * hw;
@@ -998,7 +1015,7 @@ static int project_backward_impl(int geom_kind, const float* geom, int nangles, 
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather, ws.fnorm)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
         P.im_in = im + (size_t)b0 * hw;
@@ -1081,7 +1098,7 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
         VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
-        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather)) return rc;
+        if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather, ws.fnorm)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
         fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);

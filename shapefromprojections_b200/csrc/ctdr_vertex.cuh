@@ -198,11 +198,35 @@ k_vertex_transform(const VertexParams P, float4* __restrict__ vt) {
 // boundary) come out of the same pass while the projected vertices are still in registers.
 // FULL = false (gather mode of the raster kernels): only the boxes are written — the pixel box of every face, which
 // also carries the facing sign (pack_box), and the chunk boxes; p6 / len3 / ff are not materialised at all.
+// World-space face normals of the *_VEC geometries (fp_vecs.py:85-91), angle-independent: formed once per call
+// instead of once per (angle, face) by k_face_assemble<false>.
+__global__ void __launch_bounds__(256)
+k_face_normals(const float* __restrict__ verts, const int* __restrict__ faces, int F, float4* __restrict__ fnorm) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+    const float x0 = __ldg(verts + 3 * i0), y0 = __ldg(verts + 3 * i0 + 1), z0 = __ldg(verts + 3 * i0 + 2);
+    const float x1 = __ldg(verts + 3 * i1), y1 = __ldg(verts + 3 * i1 + 1), z1 = __ldg(verts + 3 * i1 + 2);
+    const float x2 = __ldg(verts + 3 * i2), y2 = __ldg(verts + 3 * i2 + 1), z2 = __ldg(verts + 3 * i2 + 2);
+    const float e1x = __fsub_rn(x1, x0), e1y = __fsub_rn(y1, y0), e1z = __fsub_rn(z1, z0);
+    const float e2x = __fsub_rn(x2, x0), e2y = __fsub_rn(y2, y0), e2z = __fsub_rn(z2, z0);
+    fnorm[f] = make_float4(__fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y)),
+                           __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z)),
+                           __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x)), 0.0f);
+}
+
+// fnorm (FULL = false, *_VEC geometries; may be null): the face normals of k_face_normals.  Only the SIGN of
+// front_facing leaves this kernel then, and for the cone geometry it is decided without the three IEEE divisions of
+// the unit ray (fp_vecs.py:145) whenever that is safe:  facing_ref = fl-sum of fl(fl(R_i/len) * n_i) differs from
+// (R . n)/len by at most 4.1 u * sum|R_i n_i| / len (u = 2^-24: one rounding each for the quotient and the product,
+// two for the sums), and E = fma-chain of R . n from sum R_i n_i by at most 3 u * sum|R_i n_i|; so when
+// |E| > 1e-6 * sum|R_i n_i| (16.8 u, twice the 7.1 u needed) + 1e-30, facing_ref is non-zero and has the sign of E
+// (len > 0).  Faces seen edge-on within that margin — and anything with a NaN — take the reference's own sequence.
 template <bool FULL>
 __global__ void __launch_bounds__(256)
 k_face_assemble(const VertexParams P, const float4* __restrict__ vt, const int* __restrict__ labels2,
                 float* __restrict__ p6, float* __restrict__ len3, float* __restrict__ ff,
-                short4* __restrict__ face_box, short4* __restrict__ chunk_box) {
+                short4* __restrict__ face_box, short4* __restrict__ chunk_box, const float4* __restrict__ fnorm = nullptr) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     int x0 = BOX_EMPTY_LO, y0 = BOX_EMPTY_LO, x1 = -1, y1 = -1;
     if (f < P.F) {
@@ -217,6 +241,23 @@ k_face_assemble(const VertexParams P, const float4* __restrict__ vt, const int* 
         const float e1x = __fsub_rn(bb.w, a.w), e1y = __fsub_rn(yb, ya);
         const float e2x = __fsub_rn(c.w, a.w), e2y = __fsub_rn(yc, ya);
         facing = -__fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    } else if (!FULL && fnorm) {
+        const float4 nrm = __ldg(fnorm + f);
+        const AngleConst A = angle_const(P, b);
+        if (P.kind == 1) {
+            facing = __fadd_rn(__fadd_rn(__fmul_rn(A.Sx, nrm.x), __fmul_rn(A.Sy, nrm.y)), __fmul_rn(A.Sz, nrm.z));
+        } else {
+            const float Rx = __fsub_rn(__ldg(P.verts + 3 * i0), A.Sx), Ry = __fsub_rn(__ldg(P.verts + 3 * i0 + 1), A.Sy),
+                        Rz = __fsub_rn(__ldg(P.verts + 3 * i0 + 2), A.Sz);                       // fp_vecs.py:141
+            const float E = fmaf(Rz, nrm.z, fmaf(Ry, nrm.y, Rx * nrm.x));
+            const float mag = fmaf(fabsf(Rz), fabsf(nrm.z), fmaf(fabsf(Ry), fabsf(nrm.y), fabsf(Rx * nrm.x)));
+            if (fabsf(E) > fmaf(1e-6f, mag, 1e-30f)) {
+                facing = E;                                                                  // sign only
+            } else {                                                                         // edge-on within rounding, or NaN
+                const float rx = __fdiv_rn(Rx, a.z), ry = __fdiv_rn(Ry, a.z), rz = __fdiv_rn(Rz, a.z);   // :145
+                facing = __fadd_rn(__fadd_rn(__fmul_rn(rx, nrm.x), __fmul_rn(ry, nrm.y)), __fmul_rn(rz, nrm.z));
+            }
+        }
     } else {
         const float x0 = __ldg(P.verts + 3 * i0), y0 = __ldg(P.verts + 3 * i0 + 1), z0 = __ldg(P.verts + 3 * i0 + 2);
         const float x1 = __ldg(P.verts + 3 * i1), y1 = __ldg(P.verts + 3 * i1 + 1), z1 = __ldg(P.verts + 3 * i1 + 2);
