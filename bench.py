@@ -297,6 +297,19 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
     launches = (L.ctdr_launch_count() - launches0) + args.steps * xch.kernels_per_exchange(world)
     if xch.peer is not None:
         assert xch.peer.status() == 0, "peer all-reduce gave up waiting for a rank: the sums are invalid"
+    if world > 1:
+        # the exchange really summed over the ranks: one more step WITHOUT it, local sums added up by a plain
+        # all-reduce of a fresh tensor, against what the timed steps left in the exchange buffers
+        reduced = xch.scalars.clone(); g_reduced = xch.flat.double().sum(); g_mag = xch.flat.double().abs().sum()
+        xch.zero_()
+        R.project_residual_step(gd, verts, faces32, labels, mus, idx, target, phat=phat,
+                                grad_verts=xch.grad_verts, grad_mus=xch.grad_mus, out2=xch.scalars)
+        chk = torch.cat([xch.scalars, xch.flat.double().sum().reshape(1)])
+        dist.all_reduce(chk)
+        assert chk[1].item() == reduced[1].item() and abs(chk[0].item() - reduced[0].item()) <= 1e-9 * abs(chk[0].item()), \
+            f"gradient exchange did not sum over the ranks: {reduced.tolist()} vs {chk.tolist()}"
+        assert abs(chk[2].item() - g_reduced.item()) <= 1e-5 * g_mag.item() + 1e-12, (chk[2].item(), g_reduced.item(), g_mag.item())
+        xch.scalars.copy_(reduced)
     clocks = sampler.stop() if rank == 0 else None
     pixels = NA * H * W
     value = pixels / (ms_step / 1e3) / 1e9

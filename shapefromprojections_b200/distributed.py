@@ -182,7 +182,7 @@ class GradientExchange:
     def collective(self) -> str:
         if not self._active():
             return "none (one rank)"
-        return "k_peer_allreduce: one launch over NVLink peer memory" if self.peer is not None else "NCCL all-reduce (one group)"
+        return "k_peer_allreduce: one launch over NVLink peer memory" if self.peer is not None else "NCCL all-reduce (fp32 buffer + fp64 pair)"
 
     def zero_(self):
         self.storage.zero_()
@@ -192,18 +192,12 @@ class GradientExchange:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def all_reduce_tensors(self, flat, scalars):
-        """SUM over ranks of an fp32 buffer and an fp64 pair as one grouped launch where the backend can."""
+        """SUM over ranks of an fp32 buffer and an fp64 pair through the process group: two plain all-reduces.
+        (torch's ``_coalescing_manager(device=...)`` around the pair returned WITHOUT reducing for these mixed
+        dtypes on torch 2.11 / NCCL 2.28 — caught by tests/test_gpu_multi_rank.py on two GPUs — so the library
+        path stays the simple one; the one-launch exchange is ``PeerAllReduce``.)"""
         if not self._active():
             return
-        manager = getattr(dist, "_coalescing_manager", None)
-        if manager is not None and dist.get_backend() == "nccl":
-            try:
-                with manager(device=flat.device):
-                    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-                    dist.all_reduce(scalars, op=dist.ReduceOp.SUM)
-                return
-            except (TypeError, RuntimeError):                 # API drift between torch versions: two plain calls
-                pass
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         dist.all_reduce(scalars, op=dist.ReduceOp.SUM)
 
@@ -217,7 +211,7 @@ class GradientExchange:
     def kernels_per_exchange(self, world: int) -> int:
         """Kernels one zero_() + all_reduce() enqueues besides the library's own (for launch accounting): the fill,
         plus the NCCL group when the peer kernel (counted by the library) is not in use."""
-        return 1 + (1 if world > 1 and self.peer is None else 0)
+        return 1 + (2 if world > 1 and self.peer is None else 0)
 
     def loss_sum_and_count(self):
         return tuple(float(x) for x in self.scalars.tolist())
