@@ -85,6 +85,8 @@ struct Tuning {
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
+    int lanes = 2;               // CTDR_LANES: 1 = the residual step on the caller's stream only; 2 = angles in two halves on two streams
+    int replay_tiles = 0;        // CTDR_REPLAY_TILES: region edge of the replay kernel when the forward uses 4 x 4 tiles: 4 or 8; 0 = heuristic
     int face_normals = 1;        // CTDR_FACE_NORMALS: 0 = k_face_assemble forms the face normal and the unit ray per (angle, face) again
     int gather = 1;              // CTDR_GATHER: 1 = fused raster kernels gather corners from the per-vertex records (no p6/len3/ff), 0 = face arrays     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
     void load() {
@@ -96,6 +98,8 @@ struct Tuning {
         if (const char* e = getenv("CTDR_GRAD_PER_VERTEX")) grad_per_vertex = atoi(e);
         if (const char* e = getenv("CTDR_GATHER")) gather = atoi(e) != 0;
         if (const char* e = getenv("CTDR_FACE_NORMALS")) face_normals = atoi(e) != 0;
+        if (const char* e = getenv("CTDR_REPLAY_TILES")) replay_tiles = atoi(e);
+        if (const char* e = getenv("CTDR_LANES")) lanes = atoi(e) == 1 ? 1 : 2;
     }
 };
 Tuning& tuning() {
@@ -129,13 +133,22 @@ size_t raster_smem_bytes(int n_mus) { return (size_t)n_mus * sizeof(float); }   
 
 constexpr int MAX_SR = 4;   // super-regions per detector edge
 
-void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face_boxes, const int* slist, const int* scount) {
+// concurrent_B: angles in flight on the GPU when other launches of the same kind run beside this one (the two lanes of the
+// residual step): the grid-size heuristics look at what the machine sees, not at one lane's share
+void fill_decomposition(RasterParams& P, const short4* boxes, const short4* face_boxes, const int* slist, const int* scount, int concurrent_B = 0) {
     P.face_box = face_boxes; P.slist = slist; P.scount = scount;
     P.NC = (P.F + CHUNK - 1) / CHUNK;
-    P.RT = pick_region_tiles(P.B, P.F, P.H, P.W);
+    const int HB = concurrent_B > P.B ? concurrent_B : P.B;
+    P.RT = pick_region_tiles(HB, P.F, P.H, P.W);
     P.regions_x = (P.W + P.RT * TILE - 1) / (P.RT * TILE);
     P.regions_y = (P.H + P.RT * TILE - 1) / (P.RT * TILE);
     P.chunk_box = boxes;
+    // the replay kernel of the residual step prefers 8 x 8 tiles per CTA at every grid size (measured, config 3: -14 % on a
+    // 180-angle shard) while the forward sweep wants 4 x 4 on small grids: its regions are 2 x 2 forward regions then
+    // (neutral at 90 angles; the 1M-triangle mesh loses 9 % with it: heavy tiles, CTA-level imbalance)
+    const long long regions8 = (long long)((P.W + 8 * TILE - 1) / (8 * TILE)) * ((P.H + 8 * TILE - 1) / (8 * TILE));
+    P.rts = P.RT;
+    if (P.RT == 4 && (tuning().replay_tiles == 8 || (tuning().replay_tiles == 0 && P.F <= 300000 && regions8 * HB >= 40LL * 148))) P.rts = 8;
     P.region_major = tuning().region_major;     // region-major measured: -1.5 % on one GPU, -4 % on a 1/8 angle shard (config 3); centre-out another -0.5 % / -1.3 %
     P.sr_rx = (P.regions_x + MAX_SR - 1) / MAX_SR;
     P.sr_ry = (P.regions_y + MAX_SR - 1) / MAX_SR;
@@ -208,7 +221,8 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool l
     if (flags & CTDR_FLAG_NO_PREFILTER) {   // debug: literal fp64 divide for every candidate (never linked)
         k_raster<MODE, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
     } else if (linked && MODE == MODE_STEP) {
-        // replay-only residual/backward kernel over the batches the forward sweep recorded
+        // replay-only residual/backward kernel over the batches the forward sweep recorded; its own region size (P.rts)
+        const long long blocks = (long long)P.B * ((P.W + P.rts * TILE - 1) / (P.rts * TILE)) * ((P.H + P.rts * TILE - 1) / (P.rts * TILE));
         if (const char* e = getenv("CTDR_PROBE_CARVEOUT")) {       // probe: shared-memory carve-out in percent (L1 = the rest)
             cudaFuncSetAttribute(k_step_replay<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
         }
@@ -929,7 +943,8 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    return per * (size_t)win + project_fixed_bytes(F);
+    // two lanes of the residual step lay out one fixed part each, and an odd angle count gives the first lane one angle more
+    return per * (size_t)(win + 1) + 2 * project_fixed_bytes(F) + 512;
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -1069,39 +1084,38 @@ int ctdr_project_backward(int geom_kind, const float* geom, int nangles, const i
                                  grad_verts, grad_mus, vadj_start, vadj_corner, workspace, workspace_bytes, stats, flags, stream);
 }
 
-static int residual_step_impl(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
-                              const float* verts, int V, const int32_t* faces, int F,
-                              const int32_t* labels2, const float* mus, int n_mus, int H, int W,
-                              double spacing_x, double spacing_y, double max_sino_val,
-                              const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
-                              const int32_t* vadj_start, const int32_t* vadj_corner,
-                              void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
-                              cudaStream_t stream, StageTimer* tm) {
-    if (int rc = check_geom(geom_kind)) return rc;
-    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
-    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
-    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !target || !phat || !grad_verts || !grad_mus || !out2 || !workspace)
-        return fail(CTDR_E_NULL, "ctdr_project_residual_step: null pointer");
-    // per angle window: vertex stage once, forward raster (phat is an output the caller keeps), then the
-    // residual/backward sweep over the same staged p6/len3/ff and face boxes
-    const bool det = (flags & CTDR_FLAG_DETERMINISTIC) != 0;
-    if (det && (!vadj_start || !vadj_corner))
-        return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
-    ProjectWs ws;
-    // gather mode: corners from the vertex records, cotangents onto the vertices; the single-writer (deterministic) and
-    // debug kernels, and the per-corner gradient fallback, keep the [B,F] face arrays
-    const bool gather = !det && tuning().gather != 0 && tuning().grad_per_vertex != 0 && !(flags & CTDR_FLAG_NO_PREFILTER);
-    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws, !gather)) return rc;
+// The residual step's arguments, as the angle-window loop needs them
+struct ResidualArgs {
+    int geom_kind; const float* geom; int nangles; const int64_t* idx_angles;
+    const float* verts; int V; const int32_t* faces; int F;
+    const int32_t* labels2; const float* mus; int n_mus; int H, W;
+    double spacing_x, spacing_y, max_sino_val;
+    const float* target; float* phat; float* grad_verts; float* grad_mus; double* out2;
+    const int32_t* vadj_start; const int32_t* vadj_corner;
+    int64_t* stats; unsigned flags;
+    bool det, gather;
+    int concurrent_B;       // angles in flight over both lanes (fill_decomposition)
+};
+
+// angles [b_begin, b_end) of the step through the windows of workspace layout `ws`, enqueued on `stream`
+static int residual_windows(const ResidualArgs& A, ProjectWs& ws, int b_begin, int b_end, cudaStream_t stream, StageTimer* tm) {
+    const int geom_kind = A.geom_kind, nangles = A.nangles, V = A.V, F = A.F, n_mus = A.n_mus, H = A.H, W = A.W;
+    const float* geom = A.geom; const int64_t* idx_angles = A.idx_angles; const float* verts = A.verts; const int32_t* faces = A.faces;
+    const int32_t* labels2 = A.labels2; const float* mus = A.mus;
+    const double spacing_x = A.spacing_x, spacing_y = A.spacing_y, max_sino_val = A.max_sino_val;
+    const float* target = A.target; float* phat = A.phat; float* grad_verts = A.grad_verts; float* grad_mus = A.grad_mus; double* out2 = A.out2;
+    const int32_t* vadj_start = A.vadj_start; const int32_t* vadj_corner = A.vadj_corner;
+    int64_t* stats = A.stats; const unsigned flags = A.flags;
+    const bool det = A.det, gather = A.gather;
     const size_t hw = (size_t)H * W;
-    CTDR_MARK(tm, -1, stream);
-    for (int b0 = 0; b0 < B; b0 += ws.window) {
-        const int nb = (B - b0 < ws.window) ? (B - b0) : ws.window;
+    for (int b0 = b_begin; b0 < b_end; b0 += ws.window) {
+        const int nb = (b_end - b0 < ws.window) ? (b_end - b0) : ws.window;
         VertexParams VP = vertex_params(geom_kind, geom, nangles, idx_angles + b0, nb, verts, V, faces, F, H, W, spacing_x, spacing_y, max_sino_val);
         if (int rc = launch_angle_table(VP, ws.atab, stream)) return rc;
         if (int rc = launch_vertex_forward_staged(VP, ws.vt, labels2, ws.p6, ws.len3, ws.ff, ws.rws.face_boxes, ws.rws.boxes, stream, !gather, ws.fnorm)) return rc;
         RasterParams P = base_params(ws.p6, ws.ff, ws.len3, labels2, mus, n_mus, nb, F, H, W, (float)max_sino_val, stats);
         if (gather) use_vertex_records(P, ws.vt, faces, V);
-        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount);
+        fill_decomposition(P, ws.rws.boxes, ws.rws.face_boxes, ws.rws.slist, ws.rws.scount, A.concurrent_B);
         if (int rc = launch_chunk_bbox(P, ws.rws.boxes, ws.rws.face_boxes, stream, true)) return rc;
         CTDR_MARK(tm, CTDR_STAGE_VERTEX_FORWARD, stream);
         P.im = phat + (size_t)b0 * hw;
@@ -1152,6 +1166,82 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
         CTDR_MARK(tm, CTDR_STAGE_VERTEX_BACKWARD, stream);
     }
     return 0;
+}
+
+// A second, lowest-priority stream per host thread and device for the step's second lane (below), with the two
+// events of the fork/join.  Created on first use; event record / wait / kernel launches on it are capturable.
+struct SideLane { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool tried = false; };
+static SideLane* side_lane() {
+    constexpr int MAX_DEV = 64;
+    thread_local SideLane lanes[MAX_DEV];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    SideLane& L = lanes[dev];
+    if (!L.tried) {
+        L.tried = true;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = numerically largest = lowest priority
+        if (cudaStreamCreateWithPriority(&L.s, cudaStreamNonBlocking, lo) != cudaSuccess) { L.s = nullptr; cudaGetLastError(); }
+        if (L.s && (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess)) { L.s = nullptr; cudaGetLastError(); }
+    }
+    return L.s ? &L : nullptr;
+}
+
+static int residual_step_impl(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
+                              const float* verts, int V, const int32_t* faces, int F,
+                              const int32_t* labels2, const float* mus, int n_mus, int H, int W,
+                              double spacing_x, double spacing_y, double max_sino_val,
+                              const float* target, float* phat, float* grad_verts, float* grad_mus, double* out2,
+                              const int32_t* vadj_start, const int32_t* vadj_corner,
+                              void* workspace, size_t workspace_bytes, int64_t* stats, unsigned flags,
+                              cudaStream_t stream, StageTimer* tm) {
+    if (int rc = check_geom(geom_kind)) return rc;
+    if (int rc = check_sizes(B, F, H, W, n_mus)) return rc;
+    if (V <= 0) return fail(CTDR_E_SHAPE, "V=%d", V);
+    if (!geom || !idx_angles || !verts || !faces || !labels2 || !mus || !target || !phat || !grad_verts || !grad_mus || !out2 || !workspace)
+        return fail(CTDR_E_NULL, "ctdr_project_residual_step: null pointer");
+    // per angle window: vertex stage once, forward raster (phat is an output the caller keeps), then the
+    // residual/backward sweep over the same staged p6/len3/ff and face boxes
+    const bool det = (flags & CTDR_FLAG_DETERMINISTIC) != 0;
+    if (det && (!vadj_start || !vadj_corner))
+        return fail(CTDR_E_NULL, "CTDR_FLAG_DETERMINISTIC needs the vertex->corner adjacency (vadj_start, vadj_corner)");
+    // gather mode: corners from the vertex records, cotangents onto the vertices; the single-writer (deterministic) and
+    // debug kernels, and the per-corner gradient fallback, keep the [B,F] face arrays
+    const bool gather = !det && tuning().gather != 0 && tuning().grad_per_vertex != 0 && !(flags & CTDR_FLAG_NO_PREFILTER);
+    ResidualArgs A = {geom_kind, geom, nangles, idx_angles, verts, V, faces, F, labels2, mus, n_mus, H, W,
+                            spacing_x, spacing_y, max_sino_val, target, phat, grad_verts, grad_mus, out2,
+                            vadj_start, vadj_corner, stats, flags, det, gather, 0};
+    // Two lanes: the angles are cut in two halves that run the whole sequence (vertex stage, forward sweep, memsets,
+    // residual/backward sweep, vertex backward) on two streams, each in its own half of the workspace.  Every kernel
+    // of the sequence ends in a tail of few, long CTAs (and the vertex stage and memsets are bandwidth-bound while the
+    // sweeps are issue-bound): the second lane — lowest stream priority — fills what the first leaves idle.  Both
+    // lanes add into grad_verts / grad_mus / out2 with the atomics the kernels use anyway.  Not for the deterministic
+    // mode (fixed summation order) nor the timed variant (its stage marks are on one stream).
+    SideLane* side = (!det && !tm && B >= 2 && tuning().lanes == 2) ? side_lane() : nullptr;
+    if (side) {
+        const int B0 = (B + 1) / 2;
+        const size_t half = (workspace_bytes / 2) & ~(size_t)255;
+        ProjectWs ws0, ws1;
+        const size_t need = project_per_angle_bytes(V, F, true, H, W, !gather) + project_fixed_bytes(F);
+        if (half >= need &&
+            project_ws_layout(B0, V, F, H, W, true, workspace, half, &ws0, !gather) == 0 &&
+            project_ws_layout(B - B0, V, F, H, W, true, static_cast<char*>(workspace) + half, half, &ws1, !gather) == 0) {
+            A.concurrent_B = (ws0.window < B0 ? ws0.window : B0) + (ws1.window < B - B0 ? ws1.window : B - B0);
+            CTDR_CUDA(cudaEventRecord(side->fork, stream), "lane fork");
+            CTDR_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0), "lane fork wait");
+            int rc = residual_windows(A, ws1, B0, B, side->s, nullptr);              // enqueued first, scheduled last (priority)
+            if (!rc) rc = residual_windows(A, ws0, 0, B0, stream, nullptr);
+            // join even after an error: the caller's stream must not run ahead of work already enqueued on the side lane
+            cudaEventRecord(side->join, side->s);
+            cudaStreamWaitEvent(stream, side->join, 0);
+            return rc;
+        }
+    }
+    ProjectWs ws;
+    if (int rc = project_ws_layout(B, V, F, H, W, true, workspace, workspace_bytes, &ws, !gather)) return rc;
+    CTDR_MARK(tm, -1, stream);
+    return residual_windows(A, ws, 0, B, stream, tm);
 }
 
 int ctdr_project_residual_step(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,

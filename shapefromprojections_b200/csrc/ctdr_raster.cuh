@@ -116,6 +116,8 @@ struct RasterParams {
     int4*  xlist;           // [XLIST_CAP] {angle, face, tile x0, tile y0}
     int*   xcount;          // entries appended (may exceed XLIST_CAP: the region is then left to the walking kernel)
     int    bcap;            // records per angle
+    int rts;                // k_step_replay: tiles per edge of ITS regions, a multiple of RT (its CTAs amortise their wind-down over
+                            // more tiles than the forward's do; the records are per tile, only the region flags are per forward region)
     int region_major;       // CTA order, see k_raster
     int direct_max_box;     // batches whose largest in-tile face box has at most this many pixels take the direct walk
 };
@@ -230,11 +232,12 @@ __device__ __forceinline__ int centre_out(int k, int n) {
     const int c = n >> 1;
     return (k & 1) ? c - ((k + 1) >> 1) : c + (k >> 1);
 }
-__device__ __forceinline__ int region_of_rank(const RasterParams& P, int rank) {
+__device__ __forceinline__ int region_of_rank(const RasterParams& P, int rank, int regions_x, int regions_y) {
     if (P.region_major != 2) return rank;
-    const int ky = rank / P.regions_x, kx = rank - ky * P.regions_x;
-    return centre_out(ky, P.regions_y) * P.regions_x + centre_out(kx, P.regions_x);
+    const int ky = rank / regions_x, kx = rank - ky * regions_x;
+    return centre_out(ky, regions_y) * regions_x + centre_out(kx, regions_x);
 }
+__device__ __forceinline__ int region_of_rank(const RasterParams& P, int rank) { return region_of_rank(P, rank, P.regions_x, P.regions_y); }
 
 // ------------------------------------------------------------------------------------------
 // shared memory
@@ -1741,13 +1744,33 @@ k_step_replay(const RasterParams P) {
     const int tid = threadIdx.x, warp = tid >> 5;
     int lane = tid & 31;
     asm volatile("mov.b32 %0, %0;" : "+r"(lane));            // pinned, see k_raster
-    const int regions = P.regions_x * P.regions_y;
+    // this kernel's regions: rts x rts tiles = sub x sub regions of the forward sweep (sub = 1 or 2)
+    const int RTS = P.rts, sub = RTS / P.RT;
+    const int sregions_x = (P.W + RTS * TILE - 1) / (RTS * TILE), sregions_y = (P.H + RTS * TILE - 1) / (RTS * TILE);
+    const int regions = sregions_x * sregions_y;
     const int b = P.region_major ? (int)(blockIdx.x % (unsigned)P.B) : (int)(blockIdx.x / (unsigned)regions);
-    const int rr = region_of_rank(P, P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions));
-    const int bflag = (int)P.bflag[(long long)b * regions + rr];
-    if (bflag == 0) return;                                   // not recorded: k_raster<MODE_STEP> walks this region
-    const int rx0 = (rr % P.regions_x) * P.RT * TILE, ry0 = (rr / P.regions_x) * P.RT * TILE;
-    const int rx1 = min(rx0 + P.RT * TILE, P.W) - 1, ry1 = min(ry0 + P.RT * TILE, P.H) - 1;
+    const int rr = region_of_rank(P, P.region_major ? (int)(blockIdx.x / (unsigned)P.B) : (int)(blockIdx.x % (unsigned)regions), sregions_x, sregions_y);
+    // what the forward sweep left for its (up to four) regions in here, one byte each: 0 = not recorded (k_raster<MODE_STEP>
+    // walks it), 1 = recorded, 2 = nothing projects into it; 0xff = outside the detector
+    unsigned flags4 = 0xffffffffu;
+    {
+        const unsigned char* fl = P.bflag + (long long)b * (P.regions_x * P.regions_y);
+        const int fx0 = (rr % sregions_x) * sub, fy0 = (rr / sregions_x) * sub;
+        for (int j = 0; j < sub; ++j)
+            for (int i = 0; i < sub; ++i)
+                if (fx0 + i < P.regions_x && fy0 + j < P.regions_y) {
+                    const unsigned v = fl[(fy0 + j) * P.regions_x + fx0 + i];
+                    flags4 = (flags4 & ~(0xffu << (8 * (2 * j + i)))) | (v << (8 * (2 * j + i)));
+                }
+    }
+    // over the regions present: none recorded or empty -> nothing to do here; all empty -> one stream over the target;
+    // all recorded -> tiles; a mixture -> tiles that look at their own region's flag
+    const bool has0 = __vcmpeq4(flags4, 0u) != 0u, has1 = __vcmpeq4(flags4, 0x01010101u) != 0u, has2 = __vcmpeq4(flags4, 0x02020202u) != 0u;
+    if (!has1 && !has2) return;
+    const bool stream_all = !has0 && !has1;
+    const bool mixed = (int)has0 + (int)has1 + (int)has2 > 1;
+    const int rx0 = (rr % sregions_x) * RTS * TILE, ry0 = (rr / sregions_x) * RTS * TILE;
+    const int rx1 = min(rx0 + RTS * TILE, P.W) - 1, ry1 = min(ry0 + RTS * TILE, P.H) - 1;
     unsigned sbase = (unsigned)__cvta_generic_to_shared(&C.warp[warp]);     // pinned in a register, see k_raster
     asm volatile("mov.b32 %0, %0;" : "+r"(sbase));
     ReplayWarpSmem& S = *reinterpret_cast<ReplayWarpSmem*>(__cvta_shared_to_generic(sbase));
@@ -1758,7 +1781,7 @@ k_step_replay(const RasterParams P) {
     if (tid == 0) C.next_tile = 0;
     __syncthreads();
     const long long base = (long long)b * P.H * P.W;
-    if (bflag == 2) {
+    if (stream_all) {
         // nothing projects into this region: phat == 0 everywhere, residual = -target, no gradient
         if (0.0f <= P.mask_hi) {
             const int rw = rx1 - rx0 + 1, rh = ry1 - ry0 + 1;
@@ -1783,16 +1806,25 @@ k_step_replay(const RasterParams P) {
         }
     } else {
         const int tiles_x = (P.W + TILE - 1) / TILE, tiles_y = (P.H + TILE - 1) / TILE;
-        const int ntiles = P.RT * P.RT;
+        const int ntiles = RTS * RTS;
         while (true) {
             int tix = 0;
             if (lane == 0) tix = atomicAdd(&C.next_tile, 1);
             tix = __shfl_sync(FULL, tix, 0);
             if (tix >= ntiles) break;
-            const int tx0 = rx0 + (tix % P.RT) * TILE, ty0 = ry0 + (tix / P.RT) * TILE;
+            const int tcol = tix % RTS, trow = tix / RTS;
+            const int tx0 = rx0 + tcol * TILE, ty0 = ry0 + trow * TILE;
             if (tx0 > rx1 || ty0 > ry1) continue;
             const int tx1 = min(tx0 + TILE - 1, rx1), ty1 = min(ty0 + TILE - 1, ry1);
-            const int roff0 = __ldg(P.bhead + ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4));
+            int roff0 = -1;
+            if (mixed) {
+                // the forward region of this tile: unrecorded -> the walking kernel's; empty -> no head was written
+                const unsigned f = (flags4 >> (8 * (2 * (trow / P.RT) + tcol / P.RT))) & 0xffu;
+                if (f == 0u) continue;
+                if (f == 1u) roff0 = __ldg(P.bhead + ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4));
+            } else {
+                roff0 = __ldg(P.bhead + ((long long)b * tiles_y + (ty0 >> 4)) * tiles_x + (tx0 >> 4));
+            }
             if (roff0 >= 0) prefetch_record(P, S.landing[0], roff0, lane);  // in flight during the tile prologue
             // residual prologue: g = d/dphat of sum_valid (target - phat)^2 = 2*(phat - target) on pixels passing
             // get_valid_mask (fp_vecs.py:10-13; a subset of the kernel's own gradient predicate,
