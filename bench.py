@@ -11,8 +11,10 @@ one optimiser iteration (ctdr/optimize.py:162-190).
 the ranks, no collective.  --config cfg2: BASELINE.json's second metric, s per optimise iteration, on the 2bunnyA
 geometry for 500 iterations (one GPU).
 Prints ONE JSON line on rank 0.  Every number is measured where its key says (no aliases): `kernels.*_ms` are the
-stages of the step as they run inside it (CUDA events between the stages, ctdr_project_residual_step_timed),
-`gpu_launches` is the library's own launch counter over the timed region.
+stages of the step's kernel sequence over all of the rank's angles on ONE stream (CUDA events between the stages,
+ctdr_project_residual_step_timed); the timed step itself runs that sequence in two lanes (two halves of the angles on
+two streams), so `ms_per_step` is a little below the sum of the stages; `gpu_launches` is the
+library's own launch counter over the timed region.
 """
 from __future__ import annotations
 
@@ -335,7 +337,10 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
         mine.append(e0.elapsed_time(e1) / 10); names.append("zero_and_all_reduce")
         mx, mn = D.reduce(mine, "max"), D.reduce(mine, "min")
         stages = {f"{n}_ms": {"max_over_ranks": a, "min_over_ranks": b} for n, a, b in zip(names, mx, mn)}
+        stage_ms = dict(zip(names, mx))
         stages["sum_of_stage_max_ms"] = sum(mx)
+        stages["note"] = ("stages timed on one stream over all of the rank's angles; the timed step runs the same sequence in "
+                          f"{1 if os.environ.get('CTDR_LANES') == '1' else 2} lane(s), overlapping each kernel's tail with the other lane")
 
     # ---- end to end: host buffers in, host results out, every step -------------------------------
     e2e = None
@@ -422,9 +427,9 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
                     "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "traffic": tj.get(key) if tj else None,
                     "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/)"}
         fwd = kernel_roofline("k_raster<MODE_FWD, linked> (forward sweep as it runs in the step: 4 B sinogram store per pixel)",
-                              stages["raster_forward_ms"]["max_over_ranks"], 4 * Bl * H * W, "k_raster<MODE_FWD>")
+                              stage_ms["raster_forward"], 4 * Bl * H * W, "k_raster<MODE_FWD>")
         bwd = kernel_roofline("k_step_replay + k_raster<MODE_STEP> twin (residual + backward sweep as it runs in the step: "
-                              "4 B phat + 4 B target per pixel)", stages["raster_step_ms"]["max_over_ranks"], 8 * Bl * H * W,
+                              "4 B phat + 4 B target per pixel)", stage_ms["raster_step"], 8 * Bl * H * W,
                               "k_step_replay")
         line["roofline"]["dominant_kernel"] = fwd
         line["roofline"]["second_kernel"] = bwd
