@@ -1,0 +1,12 @@
+set -x
+run() { # N tag cfg steps
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29501 bench.py --gpus $1 --config $3 --steps $4 --warmup 3 --no-cpu-baseline --no-optimise --no-reference-ext > gpurun_out/${2}_n${1}_${3}.json 2> gpurun_out/${2}_n${1}_${3}.err
+tail -c 300 gpurun_out/${2}_n${1}_${3}.json
+}
+run 8 v9m cfg3 20
+run 8 v9m northstar 10
+run 8 v9m cfg4 5
+run 8 v9m cfg5 3
+run 4 v9m cfg3 20
+run 2 v9m cfg3 20
+timeout 200 python -m pytest tests/test_gpu_multi_rank.py -x -q > gpurun_out/v9m_mr.log 2>&1; tail -2 gpurun_out/v9m_mr.log
