@@ -237,6 +237,8 @@ def main():
     from shapefromprojections_b200 import _lib, distributed
 
     rank, world, local_rank = distributed.init_from_env()
+    # one process per GPU: keep the rank (and the pinned host buffers it allocates) on the GPU's own socket
+    args.numa = distributed.bind_to_gpu_numa(local_rank) if world > 1 and args.impl != "reference" else "one rank: not bound"
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
@@ -412,7 +414,7 @@ def bench_step(args, torch, dist, D, rank, world, local_rank, dev):
                        "l2_policy": "inputs larger than L2 (target + sinogram shards >> 126 MB)" if Bl * H * W * 8 > 2 * 126e6
                                     else "inputs smaller than L2: the step streams its own 2 x B x H x W x 4 B of sinogram/target, nothing else is reused between steps",
                        "parallelism": f"angles sharded over {world} GPU(s) (rank r owns angles r, r+N, ...), mesh replicated",
-                       "collective": collective},
+                       "collective": collective, "host_placement": args.numa},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches) * world,
             "gpu_launches_per_rank_per_step": launches / args.steps,
             "loss": loss_sum / max(n_valid, 1.0), "n_valid": n_valid}

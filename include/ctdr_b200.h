@@ -15,7 +15,10 @@
  *     (the reference launches on the legacy default stream: diff_fp_for.cu:253);
  *   - return value: 0 ok, < 0 argument error (CTDR_E_*), > 0 a cudaError_t; a thread-local
  *     message is available from ctdr_last_error();
- *   - re-entrant, no global state besides that thread-local string;
+ *   - re-entrant; process state is limited to that thread-local string, the launch counter, the tuning overrides
+ *     read once from the environment, and — per host thread and device — one internal low-priority stream with two
+ *     events on which ctdr_project_residual_step runs the second half of its angles (joined back into `stream`
+ *     before the call returns control of it; capturable in a CUDA graph);
  *   - float32 entry points are the tuned path; the reference also dispatches double (diff_fp_for.cu:251):
  *     the *_f64 entry points below are that instantiation on the device;
  *   - sinogram / counts are [B,H,W] row-major (the reference's [B,H,W,1]); pixel offsets are 64-bit.
@@ -77,7 +80,8 @@ const char* ctdr_last_error(void);
 unsigned long long ctdr_launch_count(void);
 
 /* Tuning / debug overrides come from the environment (CTDR_REGION_TILES, CTDR_REGION_MAJOR, CTDR_DIRECT_MAX_BOX,
- * CTDR_NO_BATCH_RECORDS), read once at first use; this re-reads them (tests and tuning scripts). */
+ * CTDR_NO_BATCH_RECORDS, CTDR_LANES, CTDR_REPLAY_TILES, CTDR_FACE_NORMALS, CTDR_GATHER, CTDR_GRAD_PER_VERTEX), read once
+ * at first use; this re-reads them (tests and tuning scripts). */
 void ctdr_tuning_reload(void);
 
 /* Self-test of the one arithmetic shortcut the kernels take: fl32(k1/(k3+1e-15)) through the

@@ -29,6 +29,32 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(local_rank: int) -> str:
+    """Pin this process (and therefore its pinned host buffers, first-touch) to the CPUs NVML reports as local to GPU
+    ``local_rank``: with one process per GPU on a two-socket box, host->device copies of a rank whose pages sit on the
+    other socket cross the socket interconnect and share it with every other such rank.  Returns what was done (for
+    the bench record); never raises — a container whose cpuset does not intersect the GPU's CPUs is left alone."""
+    if os.environ.get("CTDR_NO_NUMA_BIND"):
+        return "off (CTDR_NO_NUMA_BIND)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(ncpu, 1024) + 63) // 64)
+        local = {i for i in range(64 * len(words)) if (int(words[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if not cpus:
+            return f"skipped: GPU-local CPUs ({len(local)}) are outside this process's cpuset ({len(allowed)} CPUs)"
+        if set(cpus) == set(allowed):
+            return f"all {len(allowed)} allowed CPUs are local to the GPU"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} of {len(allowed)} CPUs ({cpus[0]}-{cpus[-1]})"
+    except Exception as e:                                  # noqa: BLE001 — placement is an optimisation, never a failure
+        return f"skipped: {type(e).__name__}: {e}"
+
+
 def strided_angles(nangles: int, rank: int, world: int):
     """Angles ``rank, rank+world, ...``: every rank sees the whole orbit, so the per-angle cost
     variation (edge-on views carry fewer fragments than face-on ones) averages out; contiguous
