@@ -2239,6 +2239,10 @@ k_raster(const RasterParams P) {
                             const unsigned w = (unsigned)C.list_id[e];
                             cid = (int)(w & 0xfffffu);
                             hit = (tcol >= ((w >> 20) & 7u)) & (tcol <= ((w >> 23) & 7u)) & (trow >= ((w >> 26) & 7u)) & (trow <= (w >> 29));
+                            if (hit) {      // the chunk's 32 face boxes (two lines) travel to L1 while earlier chunks are tested
+                                prefetch_l1(fbrow + (long long)cid * CHUNK);
+                                prefetch_l1(fbrow + (long long)cid * CHUNK + 16);
+                            }
                         }
                         m = __ballot_sync(FULL, hit);
                         lb += 32;
