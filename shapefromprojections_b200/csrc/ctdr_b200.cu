@@ -85,7 +85,7 @@ struct Tuning {
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
-    int lanes = 2;               // CTDR_LANES: 1 = the residual step on the caller's stream only; 2 = angles in two halves on two streams
+    int lanes = 2;               // CTDR_LANES: 1 = the residual step on the caller's stream only; 2 (default) .. 4 = angles in that many parts on as many streams
     int replay_tiles = 0;        // CTDR_REPLAY_TILES: region edge of the replay kernel when the forward uses 4 x 4 tiles: 4 or 8; 0 = heuristic
     int face_normals = 1;        // CTDR_FACE_NORMALS: 0 = k_face_assemble forms the face normal and the unit ray per (angle, face) again
     int gather = 1;              // CTDR_GATHER: 1 = fused raster kernels gather corners from the per-vertex records (no p6/len3/ff), 0 = face arrays     // CTDR_GRAD_PER_VERTEX: 0 = per-corner gradient window (grad_p6 / grad_len3), 1 = per (angle, vertex)
@@ -99,7 +99,7 @@ struct Tuning {
         if (const char* e = getenv("CTDR_GATHER")) gather = atoi(e) != 0;
         if (const char* e = getenv("CTDR_FACE_NORMALS")) face_normals = atoi(e) != 0;
         if (const char* e = getenv("CTDR_REPLAY_TILES")) replay_tiles = atoi(e);
-        if (const char* e = getenv("CTDR_LANES")) lanes = atoi(e) == 1 ? 1 : 2;
+        if (const char* e = getenv("CTDR_LANES")) { const int v = atoi(e); lanes = v < 1 ? 1 : (v > 4 ? 4 : v); }
     }
 };
 Tuning& tuning() {
@@ -943,8 +943,8 @@ size_t ctdr_project_workspace_bytes(int B, int V, int F, int H, int W, int need_
     long long win = (long long)(budget / per);
     if (win < 1) win = 1;
     if (win > B) win = B;
-    // two lanes of the residual step lay out one fixed part each, and an odd angle count gives the first lane one angle more
-    return per * (size_t)(win + 1) + 2 * project_fixed_bytes(F) + 512;
+    // the lanes of the residual step lay out one fixed part each, and uneven splits give some lanes one angle more
+    return per * (size_t)(win + 3) + 4 * project_fixed_bytes(F) + 1024;      // up to four lanes
 }
 
 int ctdr_project_forward(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -1170,22 +1170,26 @@ static int residual_windows(const ResidualArgs& A, ProjectWs& ws, int b_begin, i
 
 // A second, lowest-priority stream per host thread and device for the step's second lane (below), with the two
 // events of the fork/join.  Created on first use; event record / wait / kernel launches on it are capturable.
-struct SideLane { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool tried = false; };
-static SideLane* side_lane() {
+constexpr int MAX_LANES = 4;
+struct SideLanes { cudaStream_t s[MAX_LANES - 1] = {}; cudaEvent_t fork = nullptr, join[MAX_LANES - 1] = {}; bool tried = false, ok = false; };
+static SideLanes* side_lanes() {
     constexpr int MAX_DEV = 64;
-    thread_local SideLane lanes[MAX_DEV];
+    thread_local SideLanes lanes[MAX_DEV];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
-    SideLane& L = lanes[dev];
+    SideLanes& L = lanes[dev];
     if (!L.tried) {
         L.tried = true;
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = numerically largest = lowest priority
-        if (cudaStreamCreateWithPriority(&L.s, cudaStreamNonBlocking, lo) != cudaSuccess) { L.s = nullptr; cudaGetLastError(); }
-        if (L.s && (cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming) != cudaSuccess)) { L.s = nullptr; cudaGetLastError(); }
+        bool ok = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; ok && k < MAX_LANES - 1; ++k)
+            ok = cudaStreamCreateWithPriority(&L.s[k], cudaStreamNonBlocking, lo) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&L.join[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        L.ok = ok;
     }
-    return L.s ? &L : nullptr;
+    return L.ok ? &L : nullptr;
 }
 
 static int residual_step_impl(int geom_kind, const float* geom, int nangles, const int64_t* idx_angles, int B,
@@ -1218,23 +1222,36 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
     // sweeps are issue-bound): the second lane — lowest stream priority — fills what the first leaves idle.  Both
     // lanes add into grad_verts / grad_mus / out2 with the atomics the kernels use anyway.  Not for the deterministic
     // mode (fixed summation order) nor the timed variant (its stage marks are on one stream).
-    SideLane* side = (!det && !tm && B >= 2 && tuning().lanes == 2) ? side_lane() : nullptr;
+    int nl = tuning().lanes;
+    if (nl > B) nl = B;
+    SideLanes* side = (!det && !tm && nl >= 2) ? side_lanes() : nullptr;
     if (side) {
-        const int B0 = (B + 1) / 2;
-        const size_t half = (workspace_bytes / 2) & ~(size_t)255;
-        ProjectWs ws0, ws1;
+        const size_t part = (workspace_bytes / nl) & ~(size_t)255;
         const size_t need = project_per_angle_bytes(V, F, true, H, W, !gather) + project_fixed_bytes(F);
-        if (half >= need &&
-            project_ws_layout(B0, V, F, H, W, true, workspace, half, &ws0, !gather) == 0 &&
-            project_ws_layout(B - B0, V, F, H, W, true, static_cast<char*>(workspace) + half, half, &ws1, !gather) == 0) {
-            A.concurrent_B = (ws0.window < B0 ? ws0.window : B0) + (ws1.window < B - B0 ? ws1.window : B - B0);
+        ProjectWs ws[MAX_LANES];
+        int begin[MAX_LANES + 1];
+        bool ok = part >= need;
+        int inflight = 0;
+        for (int k = 0; k <= nl; ++k) begin[k] = (int)((long long)B * k / nl);
+        for (int k = 0; ok && k < nl; ++k) {
+            const int nbk = begin[k + 1] - begin[k];
+            ok = project_ws_layout(nbk, V, F, H, W, true, static_cast<char*>(workspace) + (size_t)k * part, part, &ws[k], !gather) == 0;
+            if (ok) inflight += ws[k].window < nbk ? ws[k].window : nbk;
+        }
+        if (ok) {
+            A.concurrent_B = inflight;
             CTDR_CUDA(cudaEventRecord(side->fork, stream), "lane fork");
-            CTDR_CUDA(cudaStreamWaitEvent(side->s, side->fork, 0), "lane fork wait");
-            int rc = residual_windows(A, ws1, B0, B, side->s, nullptr);              // enqueued first, scheduled last (priority)
-            if (!rc) rc = residual_windows(A, ws0, 0, B0, stream, nullptr);
-            // join even after an error: the caller's stream must not run ahead of work already enqueued on the side lane
-            cudaEventRecord(side->join, side->s);
-            cudaStreamWaitEvent(stream, side->join, 0);
+            int rc = 0;
+            for (int k = nl - 1; k >= 1; --k) {          // side lanes are enqueued first and scheduled last (priority)
+                CTDR_CUDA(cudaStreamWaitEvent(side->s[k - 1], side->fork, 0), "lane fork wait");
+                if (!rc) rc = residual_windows(A, ws[k], begin[k], begin[k + 1], side->s[k - 1], nullptr);
+            }
+            if (!rc) rc = residual_windows(A, ws[0], begin[0], begin[1], stream, nullptr);
+            // join even after an error: the caller's stream must not run ahead of work already enqueued on a side lane
+            for (int k = 1; k < nl; ++k) {
+                cudaEventRecord(side->join[k - 1], side->s[k - 1]);
+                cudaStreamWaitEvent(stream, side->join[k - 1], 0);
+            }
             return rc;
         }
     }
