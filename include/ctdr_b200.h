@@ -320,7 +320,7 @@ int ctdr_project_residual_step_timed(int geom_kind, const float* geom, int nangl
  * One process per GPU.  Every rank creates a peer block, hands its 64-byte IPC handle to the other ranks (any
  * transport: torch.distributed.all_gather_object, MPI, a file), opens theirs, and then sums a local payload
  * over all ranks with ONE kernel launch that reads the peers' blocks over NVLink (one-shot all-reduce; sized
- * for payloads up to a few MB, i.e. meshes up to ~500k vertices — use a library all-reduce beyond that).
+ * for payloads up to ~1 MB, i.e. meshes up to ~80k vertices — a library all-reduce wins beyond that).
  * Sums are formed in rank order on every rank: all ranks end with bit-identical results.
  * ------------------------------------------------------------------------------------------- */
 #define CTDR_PEER_HANDLE_BYTES 64

@@ -1365,7 +1365,8 @@ int ctdr_peer_allreduce(void* const* blocks_host, int world, int rank, size_t pa
     }
     const long long nvec = (long long)((f32_bytes + f64_bytes) / 16);
     int slices = (int)((nvec + 2 * PEER_THREADS - 1) / (2 * PEER_THREADS));     // about two vectors per thread
-    slices = slices < 1 ? 1 : (slices > PEER_MAX_SLICES ? PEER_MAX_SLICES : slices);
+    // at most 48 CTAs (<= PEER_MAX_SLICES): eight emulated ranks of the single-GPU test are then still all resident on one B200
+    slices = slices < 1 ? 1 : (slices > 48 ? 48 : slices);
     k_peer_allreduce<<<slices, PEER_THREADS, 0, (cudaStream_t)stream>>>(T, world, rank, static_cast<float4*>(local),
                                                                         (long long)(f32_bytes / 16), (int)(f64_bytes / 16),
                                                                         peer_slot_bytes(payload_bytes));
