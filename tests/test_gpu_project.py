@@ -389,3 +389,53 @@ def test_linked_sweeps_equal_unlinked(cuda_lib, monkeypatch, name):
     print(f"[{name}] linked vs unlinked residual step: grad_verts rel {rel_v:.2e}, grad_mus rel {rel_m:.2e}")
     assert rel_v <= 2e-5 and gv0.norm().item() > 0
     assert rel_m <= 2e-5
+
+
+@pytest.mark.parametrize("kind", ["cone_vec", "parallel3d_vec"])
+def test_facing_sign_of_edge_on_and_degenerate_faces(cuda_lib, kind):
+    """The fused vertex stage decides the facing SIGN from R.n without the reference's divisions when that is safe and
+    falls back to the reference's own sequence otherwise (csrc/ctdr_vertex.cuh, k_face_assemble<false>).  Faces whose
+    plane contains the source of some angle (cone) / the ray direction (parallel) sit exactly in the fallback's
+    domain, as do zero-area faces: the fused sinogram and counts must equal the staged path's (exact ``ff``) bit for bit."""
+    from shapefromprojections_b200.function import rasterizer as R
+    geom = GEOMS[kind]()
+    verts, faces, labels, mus = cases.two_material_mesh(2)
+    vecs = np.asarray(geom["Vectors"], dtype=np.float64)
+    rng = np.random.default_rng(7)
+    extra_v, extra_f = [], []
+    base = verts.shape[0]
+    for k in range(240):
+        S = vecs[k % vecs.shape[0], 0:3]                          # source position (cone) / ray direction (parallel)
+        p = rng.uniform(-0.3, 0.3, 3)
+        a = rng.normal(size=3) * 0.05
+        along = (p - S) if kind == "cone_vec" else S / np.linalg.norm(S)
+        q = p + 0.04 * along / np.linalg.norm(along) * (1 if kind == "cone_vec" else 1)   # p -> q runs along the ray: the plane contains it
+        if k % 8 == 7:
+            tri = [p, p + a, p + 2 * a]                             # three collinear corners
+        elif k % 8 == 6:
+            tri = [p, p, p + a]                                     # two identical corners
+        else:
+            tri = [p, p + a, q]
+        extra_v += tri
+        extra_f.append([base + 3 * k, base + 3 * k + 1, base + 3 * k + 2])
+    verts2 = np.concatenate([verts, np.asarray(extra_v)]).astype(np.float32)
+    faces2 = np.concatenate([faces, np.asarray(extra_f)]).astype(np.int64)
+    labels2 = np.concatenate([labels, np.tile([1, 0], (len(extra_f), 1))]).astype(np.int32)
+    gd, v, f32, lab, m = setup(geom, (verts2, faces2, labels2, mus))
+    idx = torch.arange(6, device="cuda")
+    p6, len3, ff = R.vertex_forward(gd, v, f32, idx)
+    im_ref, cnt_ref, _ = R.raster_forward(p6, len3, ff, lab, m, gd.H, gd.W, gd.max_sino_val, want_cnt=True)
+    near_zero = int((ff[:, faces.shape[0]:].abs() < 1e-7 * ff.abs().max()).sum())
+    assert near_zero >= 40, near_zero                               # the construction really produces edge-on faces
+    for switch in ("1", "0"):
+        os.environ["CTDR_FACE_NORMALS"] = switch
+        try:
+            from shapefromprojections_b200 import _lib
+            _lib.reload_tuning()
+            im, cnt, _ = R.project_forward(gd, v, f32, lab, m, idx, want_cnt=True)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["CTDR_FACE_NORMALS"]
+            _lib.reload_tuning()
+        assert torch.equal(cnt, cnt_ref.squeeze(-1)), switch
+        assert torch.equal(im, im_ref.squeeze(-1)), switch
