@@ -1954,8 +1954,11 @@ k_step_facelist(const RasterParams P) {
 // batches of every tile; MODE_STEP + LINKED is a replay-only kernel (no region lists, no queues) that skips
 // the regions the forward sweep could not record — those are done by the ordinary MODE_STEP kernel, launched
 // right after it with bmode == 2, which in turn skips the recorded ones.
+// Residency: the forward sweep of the fused path (NOCNT: 23.6 KB of shared memory per CTA) fits NINE CTAs per SM as long as it
+// stays within 56 registers — measured three times in round 2: every edit that cost it a 57th register (short batch records,
+// a region weight in the record flags) dropped it to eight CTAs and cost 4-6 % of the sweep.  The launch bound pins that.
 template <int MODE, bool EXACT_DIV, bool DIRECT = false, bool STATS = true, bool LINKED = false, bool GATHER = false, bool NOCNT = false>
-__global__ void __launch_bounds__(THREADS, 8)
+__global__ void __launch_bounds__(THREADS, (NOCNT && !STATS) ? 9 : 8)
 k_raster(const RasterParams P) {
     constexpr bool RECORD = LINKED && MODE == MODE_FWD;
     constexpr bool REPLAY = LINKED && MODE == MODE_STEP;
