@@ -1287,8 +1287,7 @@ static_assert(offsetof(WarpSmem, cntv) + 64 * sizeof(int) >= 2 * TILE * PREFIX_S
 
 // per-warp shared memory of the replay-only residual/backward kernel (k_step_replay): nothing of the forward's state
 struct __align__(16) ReplayWarpSmem {
-    double pre[2 * TILE * PREFIX_STRIDE];   // E0 | E1
-    float  acc[TILE_PIX];                   // g (0 where no gradient)
+    double pre[2 * TILE * PREFIX_STRIDE];   // E0 | E1 (the g tile itself is never stored: g = differences of E0)
     int    landing[2][BREC_INTS];           // the current batch record and the next one in flight (cp.async, 16 B pieces)
 };
 __device__ __forceinline__ double* prefix_e0(ReplayWarpSmem& S) { return S.pre; }
@@ -1312,6 +1311,27 @@ __device__ __forceinline__ void build_row_prefix(WS& S, int lane) {
     const double o0 = half ? t0 : 0.0, o1 = half ? t1 : 0.0;
     __syncwarp();                                       // the overlay may still be read as forward state by a slower lane
     double* E0 = prefix_e0(S) + row * PREFIX_STRIDE + half * 8;
+    double* E1 = E0 + TILE * PREFIX_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { E0[k] = e0[k] + o0; E1[k] = e1[k] + o1; }
+    if (half) { E0[8] = p0 + o0; E1[8] = p1 + o1; }
+    __syncwarp();
+}
+
+// the same sums straight from registers: lane = (row, half row) holds its eight g values (replay kernel: the tile of g
+// is never staged in shared memory)
+__device__ __forceinline__ void build_row_prefix_regs(ReplayWarpSmem& S, const float (&g)[8], int lane) {
+    const int row = lane >> 1, half = lane & 1;
+    double e0[8], e1[8], p0 = 0.0, p1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        e0[k] = p0; e1[k] = p1;
+        p0 += (double)g[k];
+        p1 = fma((double)g[k], (double)(half * 8 + k), p1);
+    }
+    const double t0 = __shfl_sync(FULL, p0, lane & ~1), t1 = __shfl_sync(FULL, p1, lane & ~1);
+    const double o0 = half ? t0 : 0.0, o1 = half ? t1 : 0.0;
+    double* E0 = S.pre + row * PREFIX_STRIDE + half * 8;
     double* E1 = E0 + TILE * PREFIX_STRIDE;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { E0[k] = e0[k] + o0; E1[k] = e1[k] + o1; }
@@ -1829,34 +1849,47 @@ k_step_replay(const RasterParams P) {
             // residual prologue: g = d/dphat of sum_valid (target - phat)^2 = 2*(phat - target) on pixels passing
             // get_valid_mask (fp_vecs.py:10-13; a subset of the kernel's own gradient predicate,
             // diff_fp_for.cu:69-73); loss and count once per tile
-            const int col = lane & 15, r = lane >> 4;
-            float vv[TILE / 2], tt[TILE / 2];
+            // lane = (row, half row): eight consecutive pixels, as two 16-byte loads per array on whole tiles — the layout
+            // the row prefix sums are built in, so g never goes through shared memory
+            const int prow = lane >> 1, pcol = (lane & 1) * 8;
+            float vv[8], tt[8];
+            {
+                const bool rowok = ty0 + prow <= ty1;
+                const long long o = base + (long long)(ty0 + prow) * P.W + tx0 + pcol;
+                if (tx1 - tx0 == TILE - 1 && (P.W & 3) == 0) {
+                    float4 va = make_float4(-1.f, -1.f, -1.f, -1.f), vb = va, ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+                    if (rowok) {
+                        va = __ldg(reinterpret_cast<const float4*>(P.im_in + o)); vb = __ldg(reinterpret_cast<const float4*>(P.im_in + o) + 1);
+                        ta = __ldg(reinterpret_cast<const float4*>(P.target + o)); tb = __ldg(reinterpret_cast<const float4*>(P.target + o) + 1);
+                    }
+                    vv[0] = va.x; vv[1] = va.y; vv[2] = va.z; vv[3] = va.w; vv[4] = vb.x; vv[5] = vb.y; vv[6] = vb.z; vv[7] = vb.w;
+                    tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w; tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
+                } else {
 #pragma unroll
-            for (int k = 0; k < TILE / 2; ++k) {              // all 16 loads in flight before any use
-                const int row = r + 2 * k;
-                const bool ok = (ty0 + row <= ty1) && (tx0 + col <= tx1);
-                const long long o = base + (long long)(ty0 + row) * P.W + tx0 + col;
-                vv[k] = ok ? __ldg(P.im_in + o) : -1.0f;
-                tt[k] = ok ? __ldg(P.target + o) : 0.0f;
+                    for (int k = 0; k < 8; ++k) {
+                        const bool ok = rowok && (tx0 + pcol + k <= tx1);
+                        vv[k] = ok ? __ldg(P.im_in + o + k) : -1.0f;
+                        tt[k] = ok ? __ldg(P.target + o + k) : 0.0f;
+                    }
+                }
             }
             // Pipeline: while batch k is processed out of one landing zone, record k+1 is copied into the other by
             // cp.async (16-byte pieces, no register holds the data in flight).  A record carries everything the row
             // phase needs — face ids, rows and the exact coverage — so the only global loads left in the batch are the
             // per-face ones of the gradient epilogue.
             int slot = 0;
+            float g[8];
 #pragma unroll
-            for (int k = 0; k < TILE / 2; ++k) {
-                float g = 0.0f;
+            for (int k = 0; k < 8; ++k) {
+                g[k] = 0.0f;
                 if (vv[k] > -1e-6f && vv[k] <= P.mask_hi) {
                     const float diff = vv[k] - tt[k];
-                    g = 2.0f * diff;
+                    g[k] = 2.0f * diff;
                     loss_acc += (double)diff * (double)diff; nvalid_acc++;
                 }
-                S.acc[(r + 2 * k) * TILE + col] = g;
             }
-            __syncwarp();
             if (roff0 < 0) continue;                                  // no face reaches this tile
-            build_row_prefix(S, lane);
+            build_row_prefix_regs(S, g, lane);
             while (true) {
                 cp_async_wait_all();                                  // record k (issued during the prologue / a whole batch ago)
                 __syncwarp();
