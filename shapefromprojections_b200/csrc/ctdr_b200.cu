@@ -85,6 +85,7 @@ struct Tuning {
     int direct_max_box = -1;     // CTDR_DIRECT_MAX_BOX: -1 = heuristic, 0 disables the fine-mesh forward walk
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
+    int replay_carveout = -1;    // CTDR_REPLAY_CARVEOUT: preferred shared-memory carve-out of the replay kernel in percent; -1 = the driver's choice
     int lanes = 2;               // CTDR_LANES: 1 = the residual step on the caller's stream only; 2 (default) .. 4 = angles in that many parts on as many streams
     int replay_tiles = 0;        // CTDR_REPLAY_TILES: region edge of the replay kernel when the forward uses 4 x 4 tiles: 4 or 8; 0 = heuristic
     int face_normals = 1;        // CTDR_FACE_NORMALS: 0 = k_face_assemble forms the face normal and the unit ray per (angle, face) again
@@ -99,6 +100,7 @@ struct Tuning {
         if (const char* e = getenv("CTDR_GATHER")) gather = atoi(e) != 0;
         if (const char* e = getenv("CTDR_FACE_NORMALS")) face_normals = atoi(e) != 0;
         if (const char* e = getenv("CTDR_REPLAY_TILES")) replay_tiles = atoi(e);
+        if (const char* e = getenv("CTDR_REPLAY_CARVEOUT")) replay_carveout = atoi(e);
         if (const char* e = getenv("CTDR_LANES")) { const int v = atoi(e); lanes = v < 1 ? 1 : (v > 4 ? 4 : v); }
     }
 };
@@ -223,8 +225,8 @@ int launch_raster(const RasterParams& P, unsigned flags, cudaStream_t st, bool l
     } else if (linked && MODE == MODE_STEP) {
         // replay-only residual/backward kernel over the batches the forward sweep recorded; its own region size (P.rts)
         const long long blocks = (long long)P.B * ((P.W + P.rts * TILE - 1) / (P.rts * TILE)) * ((P.H + P.rts * TILE - 1) / (P.rts * TILE));
-        if (const char* e = getenv("CTDR_PROBE_CARVEOUT")) {       // probe: shared-memory carve-out in percent (L1 = the rest)
-            cudaFuncSetAttribute(k_step_replay<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        if (tuning().replay_carveout >= 0) {       // tuning probe: shared-memory carve-out in percent (L1 = the rest)
+            cudaFuncSetAttribute(k_step_replay<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().replay_carveout);
         }
         if (P.vt) {
             if (P.stats) k_step_replay<true, true><<<(unsigned)blocks, THREADS, smem, st>>>(P);
