@@ -86,6 +86,7 @@ struct Tuning {
     bool no_batch_records = false;   // CTDR_NO_BATCH_RECORDS: residual step without linked sweeps
     int grad_per_vertex = 1;
     int replay_carveout = -1;    // CTDR_REPLAY_CARVEOUT: preferred shared-memory carve-out of the replay kernel in percent; -1 = the driver's choice
+    bool lanes_explicit = false; // CTDR_LANES given: used for every call size
     int lanes = 2;               // CTDR_LANES: 1 = the residual step on the caller's stream only; 2 (default) .. 4 = angles in that many parts on as many streams
     int replay_tiles = 0;        // CTDR_REPLAY_TILES: region edge of the replay kernel when the forward uses 4 x 4 tiles: 4 or 8; 0 = heuristic
     int face_normals = 1;        // CTDR_FACE_NORMALS: 0 = k_face_assemble forms the face normal and the unit ray per (angle, face) again
@@ -101,7 +102,7 @@ struct Tuning {
         if (const char* e = getenv("CTDR_FACE_NORMALS")) face_normals = atoi(e) != 0;
         if (const char* e = getenv("CTDR_REPLAY_TILES")) replay_tiles = atoi(e);
         if (const char* e = getenv("CTDR_REPLAY_CARVEOUT")) replay_carveout = atoi(e);
-        if (const char* e = getenv("CTDR_LANES")) { const int v = atoi(e); lanes = v < 1 ? 1 : (v > 4 ? 4 : v); }
+        if (const char* e = getenv("CTDR_LANES")) { const int v = atoi(e); lanes = v < 1 ? 1 : (v > 4 ? 4 : v); lanes_explicit = true; }
     }
 };
 Tuning& tuning() {
@@ -1224,7 +1225,9 @@ static int residual_step_impl(int geom_kind, const float* geom, int nangles, con
     // sweeps are issue-bound): the second lane — lowest stream priority — fills what the first leaves idle.  Both
     // lanes add into grad_verts / grad_mus / out2 with the atomics the kernels use anyway.  Not for the deterministic
     // mode (fixed summation order) nor the timed variant (its stage marks are on one stream).
-    int nl = tuning().lanes;
+    // small calls are launch-bound: the second lane's extra launches and the fork/join cost more than the overlap wins
+    // (measured on config 3: +1.2 % at 20 angles = 21 Mpixel, -1.5 % at 45 angles = 47 Mpixel; +9 % on config 1)
+    int nl = (tuning().lanes_explicit || (long long)B * H * W >= (1LL << 25)) ? tuning().lanes : 1;
     if (nl > B) nl = B;
     SideLanes* side = (!det && !tm && nl >= 2) ? side_lanes() : nullptr;
     if (side) {

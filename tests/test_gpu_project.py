@@ -439,3 +439,35 @@ def test_facing_sign_of_edge_on_and_degenerate_faces(cuda_lib, kind):
             _lib.reload_tuning()
         assert torch.equal(cnt, cnt_ref.squeeze(-1)), switch
         assert torch.equal(im, im_ref.squeeze(-1)), switch
+
+
+@pytest.mark.parametrize("name", list(LINK_CASES))
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_lanes_of_the_residual_step_agree_with_one_lane(cuda_lib, monkeypatch, name, lanes):
+    """The residual step cut into lanes (angle parts on several streams, each in its own part of the workspace) vs the
+    same step on the caller's stream only: identical sinogram, valid count and (to float64 reassociation) loss, gradients
+    equal up to the order of the atomics.  CTDR_LANES is given explicitly, so the lanes run even at these small sizes
+    (by default calls below 2^25 pixels stay on one stream)."""
+    from shapefromprojections_b200 import _lib
+    from shapefromprojections_b200.function import rasterizer as R
+    geom, mesh = LINK_CASES[name]()
+    gd, v, f32, labels, mus = setup(geom, mesh)
+    B = geom["Vectors"].shape[0] if "Vectors" in geom else len(geom["ProjectionAngles"])
+    idx = torch.arange(B, device="cuda")
+    target = torch.rand(B, gd.H, gd.W, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    out = {}
+    for nl in (1, lanes):
+        monkeypatch.setenv("CTDR_LANES", str(nl))
+        _lib.reload_tuning()
+        try:
+            out[nl] = R.project_residual_step(gd, v, f32, labels, mus, idx, target)
+            torch.cuda.synchronize()
+        finally:
+            monkeypatch.delenv("CTDR_LANES")
+            _lib.reload_tuning()
+    (ph0, gv0, gm0, o0), (ph1, gv1, gm1, o1) = out[1], out[lanes]
+    assert torch.equal(ph0, ph1)
+    assert o0[1].item() == o1[1].item() and abs(o0[0].item() - o1[0].item()) <= 1e-12 * abs(o0[0].item())
+    rel_v = (gv1 - gv0).norm().item() / gv0.norm().item()
+    rel_m = (gm1 - gm0).norm().item() / gm0.norm().item()
+    assert rel_v <= 2e-5 and rel_m <= 2e-5 and gv0.norm().item() > 0, (rel_v, rel_m)
